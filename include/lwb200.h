@@ -1,0 +1,107 @@
+/*
+ * lwb200.h -- C ABI of liblwb200.so, the B200 (sm_100a) implementation of the Lightworks
+ * emulator probability hot path.
+ *
+ * The reference (Aegiq/lightworks v2.3.3) is pure Python and has no FFI; the interface each
+ * entry point replaces is therefore a Python method, cited per function as file:line relative
+ * to the reference root.  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LWB_E_* code otherwise;
+ *     lwb_last_error() gives the message for the calling thread.  No C++ exception crosses the ABI.
+ *   - complex numbers are interleaved (re, im) float64 pairs ("complex128"), row-major.
+ *   - U[j*m + i] is the amplitude input mode i -> output mode j (rows = outputs), exactly the
+ *     reference convention (permanent.py:175-178, slos.py:100).
+ *   - Fock states are uint8 occupation vectors of length m.
+ *   - `dtype` selects the ARITHMETIC precision: LWB_C128 (complex128) or LWB_C64 (complex64,
+ *     inputs are rounded to float on the device, results are returned as float64).
+ *   - entry points without a suffix take HOST pointers, copy in/out and return when the result is
+ *     in the caller's buffer.  `_dev` entry points take DEVICE pointers, enqueue on the handle's
+ *     stream and return without synchronising (for callers that own device memory / streams).
+ *   - the library never keeps a caller pointer after the call returns.
+ */
+#ifndef LWB200_H
+#define LWB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lwb_context* lwb_handle;
+
+enum { LWB_C128 = 0, LWB_C64 = 1 };
+enum {
+    LWB_OK = 0,
+    LWB_E_ARG = -1,      /* bad argument (ValueError in the Python shim)             */
+    LWB_E_PHOTONS = -2,  /* photon-number mismatch (PhotonNumberError / ValueError)  */
+    LWB_E_LIMIT = -3,    /* size beyond what the kernels are built for              */
+    LWB_E_CUDA = -4,     /* CUDA runtime error (BackendError)                       */
+    LWB_E_NOMEM = -5
+};
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+int lwb_create(int device, lwb_handle* out);
+int lwb_destroy(lwb_handle h);
+const char* lwb_last_error(void);
+int lwb_version(void);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the handle's own. */
+int lwb_set_stream(lwb_handle h, void* cuda_stream);
+int lwb_synchronize(lwb_handle h);
+/* Device facts for roofline reporting. */
+int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, int name_len);
+/* Kernel variant selection for n-photon permanents: lanes per permanent = 2^log_l,
+ * min resident blocks per SM = minb.  Negative values restore the default. */
+int lwb_set_tuning(int n, int log_l, int minb);
+/* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
+int lwb_launch_count(lwb_handle h, uint64_t* count);
+
+/* ---- Fock-state indexing (host, exact) ------------------------------------------------------
+ * Replaces fock_basis/_sums, lightworks/emulator/utils/state.py:22-35 (ordering contract). */
+int lwb_fock_count(int m, int n, uint64_t* count);
+int lwb_fock_rank(int m, const uint8_t* state, uint64_t* rank);
+int lwb_fock_unrank(int m, int n, uint64_t rank, uint8_t* state);
+/* SLOS (dict insertion) order of slos.py:96-103 */
+int lwb_slos_rank(int m, const uint8_t* state, uint64_t* rank);
+int lwb_slos_unrank(int m, int n, uint64_t rank, uint8_t* state);
+/* States [r0, r0+cnt) of fock_basis(m, n) enumerated on the device; states: cnt*m bytes. */
+int lwb_fock_basis(lwb_handle h, int m, int n, uint64_t r0, uint64_t cnt, uint8_t* states);
+int lwb_fock_basis_dev(lwb_handle h, int m, int n, uint64_t r0, uint64_t cnt, uint8_t* d_states);
+
+/* ---- permanents -----------------------------------------------------------------------------
+ * thewalrus.perm semantics (call site permanent.py:81): B dense n x n matrices -> B permanents. */
+int lwb_perm_matrices(lwb_handle h, const double* A, uint64_t B, int n, int dtype, double* out);
+int lwb_perm_matrices_dev(lwb_handle h, const double* d_A, uint64_t B, int n, int dtype, double* d_out);
+
+/* PermanentBackend.probability_amplitude / probability for every (input, output) pair:
+ * permanent.py:53-114, looped by simulator.py:98-104 and analyzer.py:120-151.
+ *   ins  [n_in][m], outs [n_out][m]; every state must hold the same photon number.
+ *   want_probs = 0: out is complex [n_in][n_out];  1: out is real |amp|^2 [n_in][n_out]. */
+int lwb_perm_amplitudes(lwb_handle h, const double* U, int m, const uint8_t* ins, int n_in,
+                        const uint8_t* outs, uint64_t n_out, int dtype, int want_probs, double* out);
+int lwb_perm_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
+                            const uint8_t* d_outs, uint64_t n_out, int n_photons, int dtype,
+                            int want_probs, double* d_out);
+
+/* The loop body of PermanentBackend.full_probability_distribution (permanent.py:145-150) over the
+ * rank range [r0, r0+cnt) of fock_basis(m, n): probs[k] = |<basis[r0+k]|U|in>|^2.  Output states
+ * are unranked on the device; rank ranges are the multi-GPU shard. */
+int lwb_perm_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in_state, uint64_t r0,
+                         uint64_t cnt, int dtype, double* probs);
+int lwb_perm_basis_probs_dev(lwb_handle h, const double* d_U, int m, const uint8_t* d_in_state,
+                             int n_photons, uint64_t r0, uint64_t cnt, int dtype, double* d_probs);
+
+/* One large permanent, Gray-code space split over every SM.  [q_frac_begin, q_frac_end) selects a
+ * slice rank/size of the Gray space for multi-GPU runs (0,1 = all); the caller sums the slices. */
+int lwb_perm_single(lwb_handle h, const double* A, int n, int dtype, int slice, int n_slices, double* out2);
+int lwb_perm_single_dev(lwb_handle h, const double* d_A, int n, int dtype, int slice, int n_slices,
+                        double* d_out2);
+
+/* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
+/* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */
+int lwb_fp64_peak(lwb_handle h, double* flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LWB200_H */

@@ -1,0 +1,24 @@
+"""
+lightworks_b200 -- B200 (sm_100a) implementation of the Lightworks emulator probability hot path.
+
+Public surface (mirrors lightworks.emulator.backends):
+    PermanentBackend, SLOSBackend, Backend   drop-in backend classes (backends.py)
+    install()                                 redirect lightworks.emulator.Backend to them
+    Context, default_context                  direct access to the C ABI (include/lwb200.h)
+"""
+from ._lib import (  # noqa: F401
+    LWB_C64,
+    LWB_C128,
+    BackendError,
+    Context,
+    PhotonNumberError,
+    default_context,
+    fock_count,
+    fock_rank,
+    fock_unrank,
+    set_tuning,
+    slos_rank,
+    slos_unrank,
+)
+
+__version__ = "0.1.0"

@@ -1,0 +1,283 @@
+"""
+ctypes binding of liblwb200.so (include/lwb200.h).
+
+There is no CPU fallback: if the shared library is missing, or a compute entry point is called
+without a CUDA device, the call raises.  Host-only entry points (Fock rank/unrank/count) work
+without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblwb200.so")
+
+LWB_C128, LWB_C64 = 0, 1
+LWB_E_ARG, LWB_E_PHOTONS, LWB_E_LIMIT, LWB_E_CUDA, LWB_E_NOMEM = -1, -2, -3, -4, -5
+
+
+class BackendError(Exception):
+    """Mirror of lightworks.emulator.utils.exceptions.BackendError (emulator/utils/exceptions.py:34);
+    rebound to the reference's class by lightworks_b200.install() when lightworks is importable."""
+
+
+class PhotonNumberError(Exception):
+    """Mirror of lightworks.sdk.utils.exceptions.PhotonNumberError (sdk/utils/exceptions.py:109)."""
+
+
+_exc = {"BackendError": BackendError, "PhotonNumberError": PhotonNumberError}
+
+# every symbol include/lwb200.h declares: name -> (restype, argtypes)
+_vp, _i, _u64, _dbl = C.c_void_p, C.c_int, C.c_uint64, C.c_double
+_pi, _pu64, _pdbl = C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_double)
+SIGNATURES = {
+    "lwb_create": (_i, [_i, C.POINTER(_vp)]),
+    "lwb_destroy": (_i, [_vp]),
+    "lwb_last_error": (C.c_char_p, []),
+    "lwb_version": (_i, []),
+    "lwb_set_stream": (_i, [_vp, _vp]),
+    "lwb_synchronize": (_i, [_vp]),
+    "lwb_device_info": (_i, [_vp, _pi, _pi, C.c_char_p, _i]),
+    "lwb_set_tuning": (_i, [_i, _i, _i]),
+    "lwb_launch_count": (_i, [_vp, _pu64]),
+    "lwb_fock_count": (_i, [_i, _i, _pu64]),
+    "lwb_fock_rank": (_i, [_i, _vp, _pu64]),
+    "lwb_fock_unrank": (_i, [_i, _i, _u64, _vp]),
+    "lwb_slos_rank": (_i, [_i, _vp, _pu64]),
+    "lwb_slos_unrank": (_i, [_i, _i, _u64, _vp]),
+    "lwb_fock_basis": (_i, [_vp, _i, _i, _u64, _u64, _vp]),
+    "lwb_fock_basis_dev": (_i, [_vp, _i, _i, _u64, _u64, _vp]),
+    "lwb_perm_matrices": (_i, [_vp, _vp, _u64, _i, _i, _vp]),
+    "lwb_perm_matrices_dev": (_i, [_vp, _vp, _u64, _i, _i, _vp]),
+    "lwb_perm_amplitudes": (_i, [_vp, _vp, _i, _vp, _i, _vp, _u64, _i, _i, _vp]),
+    "lwb_perm_amplitudes_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp, _u64, _i, _i, _i, _vp]),
+    "lwb_perm_basis_probs": (_i, [_vp, _vp, _i, _vp, _u64, _u64, _i, _vp]),
+    "lwb_perm_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _u64, _u64, _i, _vp]),
+    "lwb_perm_single": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "lwb_perm_single_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "lwb_fp64_peak": (_i, [_vp, _pdbl]),
+}
+
+_cdll = None
+_lock = threading.Lock()
+
+
+def cdll() -> C.CDLL:
+    """Load liblwb200.so (once).  Raises BackendError if it has not been built."""
+    global _cdll
+    with _lock:
+        if _cdll is None:
+            if not os.path.exists(LIB_PATH):
+                raise _exc["BackendError"](
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(make -C lightworks_b200/csrc).  lightworks_b200 has no CPU fallback."
+                )
+            lib = C.CDLL(LIB_PATH)
+            for name, (res, args) in SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _cdll = lib
+    return _cdll
+
+
+def _raise(rc: int):
+    msg = cdll().lwb_last_error().decode(errors="replace")
+    if rc == LWB_E_PHOTONS:
+        raise _exc["PhotonNumberError"](msg)
+    if rc in (LWB_E_ARG, LWB_E_LIMIT):
+        raise ValueError(msg)
+    raise _exc["BackendError"](msg)
+
+
+def check(rc: int):
+    if rc != 0:
+        _raise(rc)
+
+
+def ptr(a) -> C.c_void_p:
+    """Raw pointer of a numpy array, torch tensor (host or device) or int address."""
+    if a is None:
+        return C.c_void_p(0)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return C.c_void_p(a.data_ptr())  # torch tensor
+
+
+# ---- host-only helpers (no GPU needed) ------------------------------------------------------------
+def fock_count(m: int, n: int) -> int:
+    out = C.c_uint64(0)
+    check(cdll().lwb_fock_count(m, n, C.byref(out)))
+    return int(out.value)
+
+
+def _u8(state) -> np.ndarray:
+    return np.ascontiguousarray(state, dtype=np.uint8)
+
+
+def fock_rank(state) -> int:
+    s = _u8(state)
+    out = C.c_uint64(0)
+    check(cdll().lwb_fock_rank(len(s), ptr(s), C.byref(out)))
+    return int(out.value)
+
+
+def fock_unrank(m: int, n: int, rank: int) -> np.ndarray:
+    s = np.zeros(m, dtype=np.uint8)
+    check(cdll().lwb_fock_unrank(m, n, rank, ptr(s)))
+    return s
+
+
+def slos_rank(state) -> int:
+    s = _u8(state)
+    out = C.c_uint64(0)
+    check(cdll().lwb_slos_rank(len(s), ptr(s), C.byref(out)))
+    return int(out.value)
+
+
+def slos_unrank(m: int, n: int, rank: int) -> np.ndarray:
+    s = np.zeros(m, dtype=np.uint8)
+    check(cdll().lwb_slos_unrank(m, n, rank, ptr(s)))
+    return s
+
+
+# ---- device context ---------------------------------------------------------------------------------
+class Context:
+    """One lwb_handle (one GPU).  Thin, typed wrappers over the C ABI with numpy host buffers."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p(0)
+        check(cdll().lwb_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            cdll().lwb_destroy(self._h)
+            self._h = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def set_stream(self, cuda_stream: int | None):
+        check(cdll().lwb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(cdll().lwb_synchronize(self._h))
+
+    def device_info(self) -> dict:
+        sm, khz = C.c_int(0), C.c_int(0)
+        name = C.create_string_buffer(128)
+        check(cdll().lwb_device_info(self._h, C.byref(sm), C.byref(khz), name, 128))
+        return {"sm_count": sm.value, "sm_clock_khz": khz.value, "name": name.value.decode()}
+
+    def launch_count(self) -> int:
+        out = C.c_uint64(0)
+        check(cdll().lwb_launch_count(self._h, C.byref(out)))
+        return int(out.value)
+
+    def fp64_peak(self) -> float:
+        out = C.c_double(0)
+        check(cdll().lwb_fp64_peak(self._h, C.byref(out)))
+        return float(out.value)
+
+    # -- host-buffer entry points --
+    def fock_basis(self, m: int, n: int, r0: int = 0, cnt: int | None = None) -> np.ndarray:
+        cnt = fock_count(m, n) - r0 if cnt is None else cnt
+        out = np.zeros((cnt, m), dtype=np.uint8)
+        check(cdll().lwb_fock_basis(self._h, m, n, r0, cnt, ptr(out)))
+        return out
+
+    def perm_matrices(self, A, dtype: int = LWB_C128) -> np.ndarray:  # noqa: N803
+        A = np.ascontiguousarray(A, dtype=np.complex128)  # noqa: N806
+        if A.ndim != 3 or A.shape[1] != A.shape[2]:
+            raise ValueError("expected an array of shape (B, n, n)")
+        out = np.zeros(A.shape[0], dtype=np.complex128)
+        check(cdll().lwb_perm_matrices(self._h, ptr(A), A.shape[0], A.shape[1], dtype, ptr(out)))
+        return out
+
+    def perm_amplitudes(self, U, ins, outs, dtype: int = LWB_C128, probs: bool = False) -> np.ndarray:  # noqa: N803
+        U = np.ascontiguousarray(U, dtype=np.complex128)  # noqa: N806
+        ins = np.ascontiguousarray(np.atleast_2d(ins), dtype=np.uint8)
+        outs = np.ascontiguousarray(np.atleast_2d(outs), dtype=np.uint8)
+        m = U.shape[0]
+        if U.ndim != 2 or U.shape[1] != m or ins.shape[1] != m or outs.shape[1] != m:
+            raise ValueError("unitary / state dimensions do not match")
+        out = np.zeros((ins.shape[0], outs.shape[0]), dtype=np.float64 if probs else np.complex128)
+        check(cdll().lwb_perm_amplitudes(self._h, ptr(U), m, ptr(ins), ins.shape[0], ptr(outs), outs.shape[0],
+                                         dtype, int(probs), ptr(out)))
+        return out
+
+    def perm_basis_probs(self, U, in_state, r0: int = 0, cnt: int | None = None, dtype: int = LWB_C128,  # noqa: N803
+                         out: np.ndarray | None = None) -> np.ndarray:
+        U = np.ascontiguousarray(U, dtype=np.complex128)  # noqa: N806
+        s = _u8(in_state)
+        m = U.shape[0]
+        if len(s) != m:
+            raise ValueError("unitary / state dimensions do not match")
+        cnt = fock_count(m, int(s.sum())) - r0 if cnt is None else cnt
+        if out is None:
+            out = np.zeros(cnt, dtype=np.float64)
+        check(cdll().lwb_perm_basis_probs(self._h, ptr(U), m, ptr(s), r0, cnt, dtype, ptr(out)))
+        return out
+
+    def perm_single(self, A, dtype: int = LWB_C128, slice_: int = 0, n_slices: int = 1) -> complex:  # noqa: N803
+        A = np.ascontiguousarray(A, dtype=np.complex128)  # noqa: N806
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("expected a square matrix")
+        out = np.zeros(2)
+        check(cdll().lwb_perm_single(self._h, ptr(A), A.shape[0], dtype, slice_, n_slices, ptr(out)))
+        return complex(out[0], out[1])
+
+
+_default_ctx: dict[int, Context] = {}
+
+
+def default_context(device: int | None = None) -> Context:
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if "LWB_DEVICE" not in os.environ else int(os.environ["LWB_DEVICE"])
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+# ---- device-pointer entry points (torch tensors or raw addresses; async on the handle's stream) ----
+def _dev_methods():
+    def perm_matrices_dev(self, d_A, B, n, d_out, dtype=LWB_C128):  # noqa: N803
+        check(cdll().lwb_perm_matrices_dev(self._h, ptr(d_A), B, n, dtype, ptr(d_out)))
+
+    def perm_amplitudes_dev(self, d_U, m, d_ins, n_in, d_outs, n_out, n_photons, d_out, dtype=LWB_C128, probs=False):  # noqa: N803
+        check(cdll().lwb_perm_amplitudes_dev(self._h, ptr(d_U), m, ptr(d_ins), n_in, ptr(d_outs), n_out, n_photons,
+                                             dtype, int(probs), ptr(d_out)))
+
+    def perm_basis_probs_dev(self, d_U, m, d_in_state, n_photons, r0, cnt, d_probs, dtype=LWB_C128):  # noqa: N803
+        check(cdll().lwb_perm_basis_probs_dev(self._h, ptr(d_U), m, ptr(d_in_state), n_photons, r0, cnt, dtype,
+                                              ptr(d_probs)))
+
+    def perm_single_dev(self, d_A, n, d_out2, dtype=LWB_C128, slice_=0, n_slices=1):  # noqa: N803
+        check(cdll().lwb_perm_single_dev(self._h, ptr(d_A), n, dtype, slice_, n_slices, ptr(d_out2)))
+
+    def fock_basis_dev(self, m, n, r0, cnt, d_states):
+        check(cdll().lwb_fock_basis_dev(self._h, m, n, r0, cnt, ptr(d_states)))
+
+    for f in (perm_matrices_dev, perm_amplitudes_dev, perm_basis_probs_dev, perm_single_dev, fock_basis_dev):
+        setattr(Context, f.__name__, f)
+
+
+_dev_methods()
+
+
+def set_tuning(n: int, log_l: int = -1, minb: int = -1):
+    check(cdll().lwb_set_tuning(n, log_l, minb))

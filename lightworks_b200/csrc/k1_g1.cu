@@ -1,0 +1,16 @@
+// generated instantiation unit: K1 variants (N, LOG_L) compiled in this translation unit
+#include "variants.h"
+#include "perm_kernels.cuh"
+namespace lwb {
+static const K1Variant table[] = {
+    LWB_K1_ENTRY(9, 3),
+    LWB_K1_ENTRY(10, 4),
+    LWB_K1_ENTRY(11, 5),
+    LWB_K1_ENTRY(9, 2),
+    LWB_K1_ENTRY(9, 4),
+    LWB_K1_ENTRY(10, 3),
+    LWB_K1_ENTRY(10, 5),
+    LWB_K1_ENTRY(11, 4),
+};
+const K1Variant* k1_g1_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
+}  // namespace lwb

@@ -1,0 +1,11 @@
+// generated instantiation unit: K1 variants (N, LOG_L) compiled in this translation unit
+#include "variants.h"
+#include "perm_kernels.cuh"
+namespace lwb {
+static const K1Variant table[] = {
+    LWB_K1_ENTRY(15, 5),
+    LWB_K1_ENTRY(16, 5),
+    LWB_K1_ENTRY(17, 5),
+};
+const K1Variant* k1_g3_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
+}  // namespace lwb

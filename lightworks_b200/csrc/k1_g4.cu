@@ -1,0 +1,11 @@
+// generated instantiation unit: K1 variants (N, LOG_L) compiled in this translation unit
+#include "variants.h"
+#include "perm_kernels.cuh"
+namespace lwb {
+static const K1Variant table[] = {
+    LWB_K1_ENTRY(18, 5),
+    LWB_K1_ENTRY(19, 5),
+    LWB_K1_ENTRY(20, 5),
+};
+const K1Variant* k1_g4_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
+}  // namespace lwb

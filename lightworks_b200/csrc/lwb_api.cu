@@ -1,0 +1,507 @@
+// lwb_api.cu -- C ABI (include/lwb200.h) over the kernels.  Host logic only: argument checks,
+// buffer staging, kernel-variant dispatch, launch geometry.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lwb200.h"
+#include "fock.cuh"
+#include "misc_kernels.cuh"
+#include "perm_kernels.cuh"
+#include "variants.h"
+
+using namespace lwb;
+
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                 \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess) return fail(LWB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CK(expr)                 \
+    do {                         \
+        int rc_ = (expr);        \
+        if (rc_ != 0) return rc_; \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct lwb_context {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t* d_bin = nullptr;
+    Buf bU, bIn, bOut, bRes, bPart, bTmp;
+    uint64_t launches = 0;
+    std::mutex mu;
+};
+
+static uint64_t g_bin[LWB_BIN_A * LWB_BIN_B];
+static std::once_flag g_bin_once;
+static const uint64_t* host_bin() {
+    std::call_once(g_bin_once, [] { fill_binomials(g_bin); });
+    return g_bin;
+}
+
+static int ensure(lwb_handle h, Buf& b, size_t bytes) {
+    if (bytes <= b.cap) return 0;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = std::max(bytes, (size_t)4096);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) return fail(LWB_E_NOMEM, "cudaMalloc(%zu): %s", want, cudaGetErrorString(e));
+    b.cap = want;
+    (void)h;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel variant tables live in the k1_g*.cu / k2_g*.cu instantiation units (variants.h).
+static std::vector<K1Variant> g_k1;
+static const K2Variant* g_k2[LWB_K2_MAX_N + 1];
+static int g_tune_logl[LWB_K1_MAX_N + 1];
+static std::once_flag g_tables_once;
+
+static void load_tables() {
+    std::call_once(g_tables_once, [] {
+        for (int i = 0; i <= LWB_K1_MAX_N; ++i) g_tune_logl[i] = -1;
+        const K1Variant* (*k1g[])(int*) = LWB_K1_GROUPS;
+        for (auto fn : k1g) {
+            int c = 0;
+            const K1Variant* t = fn(&c);
+            for (int i = 0; i < c; ++i) g_k1.push_back(t[i]);
+        }
+        for (auto& p : g_k2) p = nullptr;
+        const K2Variant* (*k2g[])(int*) = LWB_K2_GROUPS;
+        for (auto fn : k2g) {
+            int c = 0;
+            const K2Variant* t = fn(&c);
+            for (int i = 0; i < c; ++i) g_k2[t[i].n] = &t[i];
+        }
+    });
+}
+
+static const K1Variant* pick_k1(int n) {
+    load_tables();
+    const K1Variant* def = nullptr;
+    for (const auto& v : g_k1) {
+        if (v.n != n) continue;
+        if (!def) def = &v;
+        if (g_tune_logl[n] >= 0 && v.log_l == g_tune_logl[n]) return &v;
+    }
+    return def;
+}
+
+// ---- launch helpers ----------------------------------------------------------------------------
+template <typename F>
+static int resident_blocks(lwb_handle h, F fn, size_t smem, int* out) {
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, K1_THREADS, smem));
+    if (per_sm < 1) return fail(LWB_E_LIMIT, "kernel does not fit on an SM (smem %zu)", smem);
+    *out = per_sm * h->sm_count;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* lwb_last_error(void) { return g_err.c_str(); }
+int lwb_version(void) { return 100; }
+
+int lwb_create(int device, lwb_handle* out) {
+    if (!out) return fail(LWB_E_ARG, "lwb_create: null out");
+    int count = 0;
+    CU(cudaGetDeviceCount(&count));
+    if (device < 0 || device >= count) return fail(LWB_E_ARG, "lwb_create: device %d of %d", device, count);
+    CU(cudaSetDevice(device));
+    auto* h = new lwb_context();
+    h->device = device;
+    CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    CU(cudaMalloc(&h->d_bin, sizeof g_bin));
+    CU(cudaMemcpy(h->d_bin, host_bin(), sizeof g_bin, cudaMemcpyHostToDevice));
+    load_tables();
+    *out = h;
+    return 0;
+}
+
+int lwb_destroy(lwb_handle h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (Buf* b : {&h->bU, &h->bIn, &h->bOut, &h->bRes, &h->bPart, &h->bTmp})
+        if (b->p) cudaFree(b->p);
+    if (h->d_bin) cudaFree(h->d_bin);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return 0;
+}
+
+int lwb_set_stream(lwb_handle h, void* s) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    return 0;
+}
+
+int lwb_synchronize(lwb_handle h) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, int name_len) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, h->device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (sm_clock_khz) CU(cudaDeviceGetAttribute(sm_clock_khz, cudaDevAttrClockRate, h->device));
+    if (name && name_len > 0) {
+        strncpy(name, p.name, (size_t)name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    return 0;
+}
+
+int lwb_set_tuning(int n, int log_l, int minb) {
+    (void)minb;
+    load_tables();
+    if (n < 1 || n > LWB_K1_MAX_N) return fail(LWB_E_ARG, "lwb_set_tuning: n=%d", n);
+    if (log_l >= 0) {
+        bool ok = false;
+        for (const auto& v : g_k1) ok |= (v.n == n && v.log_l == log_l);
+        if (!ok) return fail(LWB_E_ARG, "lwb_set_tuning: no variant n=%d log_l=%d", n, log_l);
+    }
+    g_tune_logl[n] = log_l;
+    return 0;
+}
+
+int lwb_launch_count(lwb_handle h, uint64_t* count) {
+    if (!h || !count) return fail(LWB_E_ARG, "null");
+    *count = h->launches;
+    return 0;
+}
+
+// ---- Fock indexing (host) ----------------------------------------------------------------------
+static int check_mn(int m, int n) {
+    if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
+    if (n < 0 || n > LWB_MAX_PHOTONS) return fail(LWB_E_LIMIT, "photons n=%d outside [0,%d]", n, LWB_MAX_PHOTONS);
+    if (m + n - 1 >= LWB_BIN_A) return fail(LWB_E_LIMIT, "m+n too large");
+    if (binom(host_bin(), m + n - 1, n) == UINT64_MAX) return fail(LWB_E_LIMIT, "Fock space exceeds 2^64");
+    return 0;
+}
+
+int lwb_fock_count(int m, int n, uint64_t* count) {
+    CK(check_mn(m, n));
+    *count = binom(host_bin(), m + n - 1, n);
+    return 0;
+}
+
+static int photons_of(const uint8_t* s, int m) {
+    int n = 0;
+    for (int i = 0; i < m; ++i) n += s[i];
+    return n;
+}
+
+int lwb_fock_rank(int m, const uint8_t* state, uint64_t* rank) {
+    int n = photons_of(state, m);
+    CK(check_mn(m, n));
+    int x[LWB_MAX_PHOTONS + 1];
+    state_to_modes(state, m, x);
+    *rank = colex_rank(host_bin(), x, n);
+    return 0;
+}
+
+int lwb_fock_unrank(int m, int n, uint64_t rank, uint8_t* state) {
+    CK(check_mn(m, n));
+    if (rank >= binom(host_bin(), m + n - 1, n)) return fail(LWB_E_ARG, "rank out of range");
+    int x[LWB_MAX_PHOTONS + 1];
+    colex_unrank(host_bin(), rank, n, m, x);
+    modes_to_state(x, n, m, state);
+    return 0;
+}
+
+int lwb_slos_rank(int m, const uint8_t* state, uint64_t* rank) {
+    int n = photons_of(state, m);
+    CK(check_mn(m, n));
+    int x[LWB_MAX_PHOTONS + 1];
+    state_to_modes(state, m, x);
+    *rank = lex_rank(host_bin(), x, n, m);
+    return 0;
+}
+
+int lwb_slos_unrank(int m, int n, uint64_t rank, uint8_t* state) {
+    CK(check_mn(m, n));
+    if (rank >= binom(host_bin(), m + n - 1, n)) return fail(LWB_E_ARG, "rank out of range");
+    int x[LWB_MAX_PHOTONS + 1];
+    lex_unrank(host_bin(), rank, n, m, x);
+    modes_to_state(x, n, m, state);
+    return 0;
+}
+
+int lwb_fock_basis_dev(lwb_handle h, int m, int n, uint64_t r0, uint64_t cnt, uint8_t* d_states) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    CK(check_mn(m, n));
+    uint64_t S = binom(host_bin(), m + n - 1, n);
+    if (r0 > S || cnt > S - r0) return fail(LWB_E_ARG, "rank range [%llu,+%llu) outside %llu",
+                                            (unsigned long long)r0, (unsigned long long)cnt, (unsigned long long)S);
+    if (cnt == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const int threads = 128;
+    const uint64_t per_thread = 32;
+    uint64_t blocks = (cnt + threads * per_thread - 1) / (threads * per_thread);
+    fock_basis_kernel<<<(unsigned)blocks, threads, 0, h->stream>>>(h->d_bin, m, n, r0, cnt, per_thread, d_states);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lwb_fock_basis(lwb_handle h, int m, int n, uint64_t r0, uint64_t cnt, uint8_t* states) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CK(check_mn(m, n));
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bOut, cnt * (uint64_t)m));
+    CK(lwb_fock_basis_dev(h, m, n, r0, cnt, (uint8_t*)h->bOut.p));
+    CU(cudaMemcpyAsync(states, h->bOut.p, cnt * (uint64_t)m, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_perm_matrices_dev(lwb_handle h, const double* d_A, uint64_t B, int n, int dtype, double* d_out) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    if (dtype != LWB_C128 && dtype != LWB_C64) return fail(LWB_E_ARG, "dtype %d", dtype);
+    if (n < 1 || n > LWB_K1_MAX_N) return fail(LWB_E_LIMIT, "batched permanents support 1 <= n <= %d (got %d)", LWB_K1_MAX_N, n);
+    if (B == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const K1Variant* v = pick_k1(n);
+    const int gpb = K1_THREADS >> v->log_l;
+    const size_t smem = (size_t)gpb * n * n * (dtype == LWB_C128 ? 16 : 8);
+    if (smem > 200 * 1024) return fail(LWB_E_LIMIT, "matrix batch tile needs %zu B of shared memory", smem);
+    auto fn = v->matrices[dtype];
+    int resident = 0;
+    CK(resident_blocks(h, fn, smem, &resident));
+    uint64_t need = (B + gpb - 1) / gpb;
+    unsigned grid = (unsigned)std::min<uint64_t>(need, (uint64_t)resident);
+    PermMatricesArgs a{(const double2*)d_A, B, d_out};
+    fn<<<grid, K1_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lwb_perm_matrices(lwb_handle h, const double* A, uint64_t B, int n, int dtype, double* out) {
+    if (!h || !A || !out) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n < 1 || n > LWB_K1_MAX_N) return fail(LWB_E_LIMIT, "batched permanents support 1 <= n <= %d (got %d)", LWB_K1_MAX_N, n);
+    if (B == 0) return 0;
+    CU(cudaSetDevice(h->device));
+    const size_t in_bytes = B * (uint64_t)n * n * 16, out_bytes = B * 16;
+    CK(ensure(h, h->bU, in_bytes));
+    CK(ensure(h, h->bRes, out_bytes));
+    CU(cudaMemcpyAsync(h->bU.p, A, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(lwb_perm_matrices_dev(h, (const double*)h->bU.p, B, n, dtype, (double*)h->bRes.p));
+    CU(cudaMemcpyAsync(out, h->bRes.p, out_bytes, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+static int launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
+                         const uint8_t* d_outs, uint64_t r0, uint64_t n_out, int n, int dtype,
+                         int want_probs, double* d_out) {
+    if (dtype != LWB_C128 && dtype != LWB_C64) return fail(LWB_E_ARG, "dtype %d", dtype);
+    if (n < 1 || n > LWB_K1_MAX_N) return fail(LWB_E_LIMIT, "batched permanents support 1 <= n <= %d photons (got %d)", LWB_K1_MAX_N, n);
+    if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
+    if (n_in < 1 || n_in > 65535) return fail(LWB_E_ARG, "n_in=%d outside [1,65535]", n_in);
+    if (n_out == 0) return 0;
+    const K1Variant* v = pick_k1(n);
+    const int gpb = K1_THREADS >> v->log_l;
+    const size_t smem = (size_t)m * n * (dtype == LWB_C128 ? 16 : 8) + (size_t)gpb * n * sizeof(int);
+    auto fn = v->states[dtype];
+    int resident = 0;
+    CK(resident_blocks(h, fn, smem, &resident));
+    uint64_t need = (n_out + gpb - 1) / gpb;
+    uint64_t gx = std::max<uint64_t>(1, (uint64_t)resident / (uint64_t)n_in);
+    gx = std::min<uint64_t>(need, gx);
+    PermStatesArgs a{(const double2*)d_U, m, d_ins, d_outs, r0, n_out, h->d_bin, d_out, want_probs};
+    dim3 grid((unsigned)gx, (unsigned)n_in, 1);
+    fn<<<grid, K1_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lwb_perm_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
+                            const uint8_t* d_outs, uint64_t n_out, int n_photons, int dtype,
+                            int want_probs, double* d_out) {
+    if (!h || !d_outs) return fail(LWB_E_ARG, "null argument");
+    CU(cudaSetDevice(h->device));
+    return launch_states(h, d_U, m, d_ins, n_in, d_outs, 0, n_out, n_photons, dtype, want_probs, d_out);
+}
+
+int lwb_perm_amplitudes(lwb_handle h, const double* U, int m, const uint8_t* ins, int n_in,
+                        const uint8_t* outs, uint64_t n_out, int dtype, int want_probs, double* out) {
+    if (!h || !U || !ins || !outs || !out) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
+    if (n_in < 1) return fail(LWB_E_ARG, "n_in=%d", n_in);
+    if (n_out == 0) return 0;
+    const int n = photons_of(ins, m);
+    for (int i = 0; i < n_in; ++i)
+        if (photons_of(ins + (size_t)i * m, m) != n) return fail(LWB_E_PHOTONS, "input %d holds a different photon number", i);
+    for (uint64_t j = 0; j < n_out; ++j)
+        if (photons_of(outs + j * m, m) != n)
+            return fail(LWB_E_PHOTONS, "output %llu holds %d photons, inputs hold %d", (unsigned long long)j,
+                        photons_of(outs + j * m, m), n);
+    const size_t per = want_probs ? 8 : 16;
+    if (n == 0) {  // perm of the 0x0 matrix = 1 (thewalrus), factorials = 1
+        for (uint64_t k = 0; k < (uint64_t)n_in * n_out; ++k) {
+            if (want_probs) out[k] = 1.0;
+            else { out[2 * k] = 1.0; out[2 * k + 1] = 0.0; }
+        }
+        return 0;
+    }
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bU, (size_t)m * m * 16));
+    CK(ensure(h, h->bIn, (size_t)n_in * m));
+    CK(ensure(h, h->bOut, n_out * (uint64_t)m));
+    CK(ensure(h, h->bRes, (size_t)n_in * n_out * per));
+    CU(cudaMemcpyAsync(h->bU.p, U, (size_t)m * m * 16, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->bIn.p, ins, (size_t)n_in * m, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->bOut.p, outs, n_out * (uint64_t)m, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, n_in, (const uint8_t*)h->bOut.p, 0,
+                     n_out, n, dtype, want_probs, (double*)h->bRes.p));
+    CU(cudaMemcpyAsync(out, h->bRes.p, (size_t)n_in * n_out * per, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_perm_basis_probs_dev(lwb_handle h, const double* d_U, int m, const uint8_t* d_in_state,
+                             int n_photons, uint64_t r0, uint64_t cnt, int dtype, double* d_probs) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    CK(check_mn(m, n_photons));
+    uint64_t S = binom(host_bin(), m + n_photons - 1, n_photons);
+    if (r0 > S || cnt > S - r0) return fail(LWB_E_ARG, "rank range outside the Fock space");
+    CU(cudaSetDevice(h->device));
+    return launch_states(h, d_U, m, d_in_state, 1, nullptr, r0, cnt, n_photons, dtype, 1, d_probs);
+}
+
+int lwb_perm_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in_state, uint64_t r0,
+                         uint64_t cnt, int dtype, double* probs) {
+    if (!h || !U || !in_state || !probs) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
+    const int n = photons_of(in_state, m);
+    CK(check_mn(m, n));
+    uint64_t S = binom(host_bin(), m + n - 1, n);
+    if (r0 > S || cnt > S - r0) return fail(LWB_E_ARG, "rank range outside the Fock space");
+    if (cnt == 0) return 0;
+    if (n == 0) { probs[0] = 1.0; return 0; }
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bU, (size_t)m * m * 16));
+    CK(ensure(h, h->bIn, (size_t)m));
+    CK(ensure(h, h->bRes, cnt * 8));
+    CU(cudaMemcpyAsync(h->bU.p, U, (size_t)m * m * 16, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->bIn.p, in_state, (size_t)m, cudaMemcpyHostToDevice, h->stream));
+    CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, 1, nullptr, r0, cnt, n, dtype, 1,
+                     (double*)h->bRes.p));
+    CU(cudaMemcpyAsync(probs, h->bRes.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_perm_single_dev(lwb_handle h, const double* d_A, int n, int dtype, int slice, int n_slices, double* d_out2) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    if (dtype != LWB_C128 && dtype != LWB_C64) return fail(LWB_E_ARG, "dtype %d", dtype);
+    if (n < 1 || n > LWB_K2_MAX_N) return fail(LWB_E_LIMIT, "single permanent supports 1 <= n <= %d (got %d)", LWB_K2_MAX_N, n);
+    if (n_slices < 1 || slice < 0 || slice >= n_slices) return fail(LWB_E_ARG, "slice %d of %d", slice, n_slices);
+    CU(cudaSetDevice(h->device));
+    load_tables();
+    if (!g_k2[n]) return fail(LWB_E_LIMIT, "no single-permanent kernel for n=%d", n);
+    const int C = g_k2[n]->chunk_bits;
+    const uint64_t Q = 1ull << (n - 1 - C);
+    const uint64_t qb = Q * (uint64_t)slice / (uint64_t)n_slices, qe = Q * (uint64_t)(slice + 1) / (uint64_t)n_slices;
+    auto fn = g_k2[n]->single[dtype];
+    int resident = 0;
+    CK(resident_blocks(h, fn, 0, &resident));
+    uint64_t need = (qe - qb + K1_THREADS - 1) / K1_THREADS;
+    unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)resident));
+    CK(ensure(h, h->bPart, (size_t)grid * 16));
+    if (qe > qb) {
+        PermSingleArgs a{(const double2*)d_A, qb, qe, (double*)h->bPart.p};
+        fn<<<grid, K1_THREADS, 0, h->stream>>>(a);
+        h->launches++;
+        CU(cudaGetLastError());
+        reduce_partials_kernel<<<1, 256, 0, h->stream>>>((const double*)h->bPart.p, (int)grid, d_out2);
+    } else {
+        reduce_partials_kernel<<<1, 256, 0, h->stream>>>((const double*)h->bPart.p, 0, d_out2);
+    }
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lwb_perm_single(lwb_handle h, const double* A, int n, int dtype, int slice, int n_slices, double* out2) {
+    if (!h || !A || !out2) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (n < 1 || n > LWB_K2_MAX_N) return fail(LWB_E_LIMIT, "single permanent supports 1 <= n <= %d (got %d)", LWB_K2_MAX_N, n);
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bU, (size_t)n * n * 16));
+    CK(ensure(h, h->bRes, 16));
+    CU(cudaMemcpyAsync(h->bU.p, A, (size_t)n * n * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(lwb_perm_single_dev(h, (const double*)h->bU.p, n, dtype, slice, n_slices, (double*)h->bRes.p));
+    CU(cudaMemcpyAsync(out2, h->bRes.p, 16, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_fp64_peak(lwb_handle h, double* flops_per_s) {
+    if (!h || !flops_per_s) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bTmp, 8 * 1024));
+    const int iters = 4096, blocks = h->sm_count * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, h->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, h->stream>>>((double*)h->bTmp.p, iters, 1.0000001);
+        h->launches++;
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * DFMA_PER_ITER * (double)iters * blocks * threads / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, flops);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *flops_per_s = best;
+    return 0;
+}
+
+}  // extern "C"

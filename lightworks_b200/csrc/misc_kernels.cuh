@@ -1,0 +1,42 @@
+// misc_kernels.cuh -- on-device Fock enumeration and the FP64 peak micro-benchmark.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fock.cuh"
+
+namespace lwb {
+
+// States [r0, r0+cnt) of the reference's fock_basis(m, n) order (emulator/utils/state.py:22-35):
+// each thread unranks the first state of its slice and walks the colex successor.
+static __global__ void fock_basis_kernel(const uint64_t* __restrict__ bin, int m, int n, uint64_t r0, uint64_t cnt,
+                                  uint64_t per_thread, uint8_t* __restrict__ states) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint64_t k = t * per_thread;
+    if (k >= cnt) return;
+    const uint64_t k_end = (k + per_thread < cnt) ? k + per_thread : cnt;
+    int x[LWB_MAX_PHOTONS + 1];
+    colex_unrank(bin, r0 + k, n, m, x);
+    for (; k < k_end; ++k) {
+        uint8_t* s = states + k * (uint64_t)m;
+        for (int i = 0; i < m; ++i) s[i] = 0;
+        for (int i = 0; i < n; ++i) s[x[i]] += 1;
+        colex_next(x, n, m);
+    }
+}
+
+// FP64 roofline denominator: 8 independent DFMA chains per thread, no memory traffic.
+constexpr int DFMA_PER_ITER = 8;
+static __global__ void dfma_peak_kernel(double* out, int iters, double a) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    const double b = 1e-9;
+#pragma unroll 8
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;  // keep the chains alive
+}
+
+}  // namespace lwb

@@ -1,0 +1,289 @@
+// perm_kernels.cuh -- batched and single-permanent kernels built on glynn_chunk.
+//
+//  K1s perm_states_kernel   : amplitudes <out|U|in> for inputs x outputs given as Fock states, or for
+//                             a rank range of the reference's fock_basis order enumerated on-device.
+//                             Replaces the loops at permanent.py:145-157, simulator.py:98-104,
+//                             analyzer.py:120-151 (per-pair partition + perm + factorial scaling).
+//  K1m perm_matrices_kernel : permanents of B dense n x n matrices (thewalrus.perm semantics).
+//  K2  perm_single_kernel   : one large permanent, Gray space split over every lane of the GPU
+//                             (and over ranks through [q_begin, q_end)).
+#pragma once
+#include "fock.cuh"
+#include "glynn.cuh"
+
+namespace lwb {
+
+constexpr int K1_THREADS = 256;
+
+// Work split shared by all kernels: LOG_L lanes-per-permanent exponent and chunk bits.
+template <int N, int LOG_L>
+struct K1Shape {
+    static constexpr int L = 1 << LOG_L;
+    static constexpr int C = N - 1 - LOG_L;          // steps per lane = 2^C
+    static constexpr int U = C < 2 ? C : 2;          // statically unrolled low bits
+    static constexpr int GPB = K1_THREADS / L;       // groups (permanents in flight) per block
+};
+
+struct PermStatesArgs {
+    const double2* U;          // m x m complex128, row-major, device
+    int m;
+    const uint8_t* in_states;  // [n_in][m]
+    const uint8_t* out_states; // [n_out][m] or nullptr -> basis mode
+    uint64_t r0;               // basis mode: first rank
+    uint64_t n_out;
+    const uint64_t* bin;       // binomial table (device)
+    double* out;               // [n_in][n_out] complex (2 doubles) or real
+    int out_probs;             // 0: amplitudes, 1: |amp|^2
+};
+
+template <typename T>
+__device__ __forceinline__ T group_sum(T v, int log_l) {
+    for (int s = 0; s < log_l; ++s) v += __shfl_xor_sync(0xffffffffu, v, 1 << s);
+    return v;
+}
+
+template <int N, int LOG_L, typename T>
+__global__ void __launch_bounds__(K1_THREADS) perm_states_kernel(PermStatesArgs a) {
+    using S = K1Shape<N, LOG_L>;
+    using V = typename vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* Vs = reinterpret_cast<V*>(smem_raw);                        // [m][N]
+    int* rowidx_all = reinterpret_cast<int*>(Vs + (size_t)a.m * N);  // [GPB][N]
+    __shared__ int incol[N];
+    __shared__ double fin_s;
+
+    const int tid = threadIdx.x;
+    const int m = a.m;
+    const uint8_t* ins = a.in_states + (size_t)blockIdx.y * m;
+    if (tid == 0) {
+        int c = 0;
+        double f = 1.0;
+        for (int i = 0; i < m; ++i)
+            for (int k = 0; k < ins[i]; ++k) {
+                if (c < N) incol[c] = i;
+                ++c;
+                f *= (double)(k + 1);
+            }
+        fin_s = f;
+    }
+    __syncthreads();
+    for (int e = tid; e < m * N; e += K1_THREADS) {
+        int r = e / N, c = e - r * N;
+        double2 u = a.U[(size_t)r * m + incol[c]];
+        V v;
+        v.x = (T)u.x;
+        v.y = (T)u.y;
+        Vs[e] = v;
+    }
+
+    const int g_in_blk = tid >> LOG_L;
+    const int lane_g = tid & (S::L - 1);
+    int* rowidx = rowidx_all + g_in_blk * N;
+    const uint64_t total_groups = (uint64_t)gridDim.x * S::GPB;
+    const uint64_t gid = (uint64_t)blockIdx.x * S::GPB + g_in_blk;
+    const uint64_t it_begin = (a.n_out * gid) / total_groups;
+    const uint64_t it_end = (a.n_out * (gid + 1)) / total_groups;
+    const uint64_t max_len = (a.n_out + total_groups - 1) / total_groups;
+    const uint64_t my_len = it_end - it_begin;
+
+    double fout = 1.0;
+    if (lane_g == 0) {
+        int x[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) x[i] = 0;
+        if (my_len > 0) {
+            if (a.out_states) {
+                const uint8_t* os = a.out_states + it_begin * m;
+                int c = 0;
+                for (int i = 0; i < m; ++i)
+                    for (int k = 0; k < os[i]; ++k) {
+                        if (c < N) x[c] = i;
+                        ++c;
+                        fout *= (double)(k + 1);
+                    }
+            } else {
+                colex_unrank(a.bin, a.r0 + it_begin, N, m, x);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < N; ++i) rowidx[i] = x[i] * N;
+    }
+    __syncthreads();
+
+    const double fin = fin_s;
+    double* outp = a.out + (size_t)blockIdx.y * a.n_out * (a.out_probs ? 1 : 2);
+
+    for (uint64_t it = 0; it < max_len; ++it) {
+        const bool active = it < my_len;
+        T sr = T(0), si = T(0);
+        glynn_chunk<N, S::C, S::U, T>(Vs, rowidx, (uint32_t)lane_g, sr, si);
+        double dr = group_sum<double>((double)sr, LOG_L);
+        double di = group_sum<double>((double)si, LOG_L);
+        __syncwarp();
+        if (lane_g == 0 && active) {
+            if (!a.out_states) {  // factorials of the current occupation (runs of equal modes)
+                fout = 1.0;
+                int run = 1;
+#pragma unroll
+                for (int i = 1; i < N; ++i) {
+                    run = (rowidx[i] == rowidx[i - 1]) ? run + 1 : 1;
+                    fout *= (double)run;
+                }
+            }
+            const double scale = sqrt(fin * fout);
+            const double re = (2.0 * dr) / scale, im = (2.0 * di) / scale;
+            const uint64_t o = it_begin + it;
+            if (a.out_probs) outp[o] = re * re + im * im;
+            else { outp[2 * o] = re; outp[2 * o + 1] = im; }
+            // advance to the next output state
+            if (it + 1 < my_len) {
+                if (a.out_states) {
+                    const uint8_t* os = a.out_states + (o + 1) * m;
+                    int c = 0;
+                    fout = 1.0;
+                    for (int i = 0; i < m; ++i)
+                        for (int k = 0; k < os[i]; ++k) {
+                            if (c < N) rowidx[c] = i * N;
+                            ++c;
+                            fout *= (double)(k + 1);
+                        }
+                } else {
+                    // colex successor on the mode list (units of N)
+                    for (int p = 0; p < N; ++p) {
+                        const int lim = (p == N - 1) ? (m - 1) * N : rowidx[p + 1];
+                        if (rowidx[p] < lim) {
+                            rowidx[p] += N;
+                            for (int q = 0; q < p; ++q) rowidx[q] = 0;
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PermMatricesArgs {
+    const double2* A;  // [B][n][n] complex128 row-major, device
+    uint64_t B;
+    double* out;       // [B][2]
+};
+
+template <int N, int LOG_L, typename T>
+__global__ void __launch_bounds__(K1_THREADS) perm_matrices_kernel(PermMatricesArgs a) {
+    using S = K1Shape<N, LOG_L>;
+    using V = typename vec2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    V* Ms_all = reinterpret_cast<V*>(smem_raw);  // [GPB][N*N]
+    __shared__ int ident[N];
+    const int tid = threadIdx.x;
+    if (tid < N) ident[tid] = tid * N;
+    const int g_in_blk = tid >> LOG_L;
+    const int lane_g = tid & (S::L - 1);
+    V* Ms = Ms_all + (size_t)g_in_blk * N * N;
+    const uint64_t total_groups = (uint64_t)gridDim.x * S::GPB;
+    const uint64_t gid = (uint64_t)blockIdx.x * S::GPB + g_in_blk;
+    const uint64_t iters = (a.B + total_groups - 1) / total_groups;
+    __syncthreads();
+    for (uint64_t it = 0; it < iters; ++it) {
+        const uint64_t b = gid + it * total_groups;
+        const bool active = b < a.B;
+        __syncwarp();
+        if (active) {
+            const double2* src = a.A + b * (uint64_t)(N * N);
+            for (int e = lane_g; e < N * N; e += S::L) {
+                double2 u = src[e];
+                V v;
+                v.x = (T)u.x;
+                v.y = (T)u.y;
+                Ms[e] = v;
+            }
+        } else if (it == 0) {
+            for (int e = lane_g; e < N * N; e += S::L) { V v; v.x = T(0); v.y = T(0); Ms[e] = v; }
+        }
+        __syncwarp();
+        T sr = T(0), si = T(0);
+        glynn_chunk<N, S::C, S::U, T>(Ms, ident, (uint32_t)lane_g, sr, si);
+        double dr = group_sum<double>((double)sr, LOG_L);
+        double di = group_sum<double>((double)si, LOG_L);
+        if (lane_g == 0 && active) {
+            a.out[2 * b] = 2.0 * dr;
+            a.out[2 * b + 1] = 2.0 * di;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct PermSingleArgs {
+    const double2* A;   // [n][n]
+    uint64_t q_begin, q_end;  // chunk range handled by this launch (this rank)
+    double* partials;   // [gridDim.x][2]
+};
+
+template <int N>
+struct K2Shape {
+    static constexpr int C0 = N - 16;
+    static constexpr int C = C0 < 4 ? (N - 1 < 4 ? N - 1 : 4) : (C0 > 10 ? 10 : C0);
+    static constexpr int U = C < 2 ? C : 2;
+};
+
+template <int N, typename T>
+__global__ void __launch_bounds__(K1_THREADS) perm_single_kernel(PermSingleArgs a) {
+    using S = K2Shape<N>;
+    using V = typename vec2<T>::type;
+    __shared__ __align__(16) V Ms[N * N];
+    __shared__ int ident[N];
+    __shared__ double red[2][K1_THREADS / 32];
+    const int tid = threadIdx.x;
+    if (tid < N) ident[tid] = tid * N;
+    for (int e = tid; e < N * N; e += K1_THREADS) {
+        double2 u = a.A[e];
+        V v;
+        v.x = (T)u.x;
+        v.y = (T)u.y;
+        Ms[e] = v;
+    }
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * K1_THREADS;
+    // every lane of a warp runs the same number of chunks (uniform control flow for broadcast reads);
+    // lanes past q_end redo the last chunk with weight 0
+    double dr = 0.0, di = 0.0;
+    const uint64_t warp_first = a.q_begin + (uint64_t)blockIdx.x * K1_THREADS + (tid & ~31);
+    for (uint64_t qw = warp_first; qw < a.q_end; qw += stride) {
+        uint64_t q = qw + (tid & 31);
+        const bool live = q < a.q_end;
+        if (!live) q = a.q_end - 1;
+        T sr = T(0), si = T(0);
+        glynn_chunk<N, S::C, S::U, T>(Ms, ident, (uint32_t)q, sr, si);
+        if (live) { dr += (double)sr; di += (double)si; }
+    }
+    dr = group_sum<double>(dr, 5);
+    di = group_sum<double>(di, 5);
+    if ((tid & 31) == 0) { red[0][tid >> 5] = dr; red[1][tid >> 5] = di; }
+    __syncthreads();
+    if (tid == 0) {
+        double r = 0.0, i = 0.0;
+        for (int w = 0; w < K1_THREADS / 32; ++w) { r += red[0][w]; i += red[1][w]; }
+        a.partials[2 * blockIdx.x] = r;
+        a.partials[2 * blockIdx.x + 1] = i;
+    }
+}
+
+// fixed-order final reduction: out = 2 * sum(partials)   (perm = 2 * sum_g sign_g prod_j w_j)
+static __global__ void reduce_partials_kernel(const double* partials, int n, double* out) {
+    __shared__ double sr[256], si[256];
+    double r = 0.0, i = 0.0;
+    for (int k = threadIdx.x; k < n; k += 256) { r += partials[2 * k]; i += partials[2 * k + 1]; }
+    sr[threadIdx.x] = r;
+    si[threadIdx.x] = i;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) { sr[threadIdx.x] += sr[threadIdx.x + s]; si[threadIdx.x] += si[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = 2.0 * sr[0]; out[1] = 2.0 * si[0]; }
+}
+
+}  // namespace lwb
