@@ -45,8 +45,9 @@ int lwb_create(int device, lwb_handle* out);
 int lwb_destroy(lwb_handle h);
 const char* lwb_last_error(void);
 int lwb_version(void);
-/* Run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the handle's own. */
-int lwb_set_stream(lwb_handle h, void* cuda_stream);
+/* Run on a caller-owned CUDA stream (cudaStream_t as void*; NULL = the legacy default stream).
+ * use_own != 0 restores the handle's own non-blocking stream. */
+int lwb_set_stream(lwb_handle h, void* cuda_stream, int use_own);
 int lwb_synchronize(lwb_handle h);
 /* Device facts for roofline reporting. */
 int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, int name_len);
@@ -96,6 +97,30 @@ int lwb_perm_basis_probs_dev(lwb_handle h, const double* d_U, int m, const uint8
 int lwb_perm_single(lwb_handle h, const double* A, int n, int dtype, int slice, int n_slices, double* out2);
 int lwb_perm_single_dev(lwb_handle h, const double* d_A, int n, int dtype, int slice, int n_slices,
                         double* d_out2);
+
+/* ---- SLOS ------------------------------------------------------------------------------------
+ * SLOSBackend.calculate (slos.py:82-105): amplitude of every output state of C(m+n-1, n).
+ *   order 0: fock_basis (reference permanent) order; order 1: SLOS dict-insertion order.
+ *   amps: S complex.  in_state is always a HOST pointer (it drives the layer loop). */
+int lwb_slos_amplitudes(lwb_handle h, const double* U, int m, const uint8_t* in_state, int order, double* amps);
+int lwb_slos_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order,
+                            double* d_amps);
+/* |amplitude|^2 of every output state, same orders (the loop body of slos.py:73-74 without filtering). */
+int lwb_slos_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in_state, int order, double* probs);
+int lwb_slos_basis_probs_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order,
+                             double* d_probs);
+
+/* ---- full distributions -------------------------------------------------------------------------
+ * {Permanent,SLOS}Backend.full_probability_distribution (permanent.py:116-163, slos.py:43-80) for a
+ * compiled circuit with m_tot = n_modes + loss_modes modes: vacuum shortcut, loss-mode zero padding,
+ * zero-real-photon skip (permanent only), strict p > threshold, loss-mode marginalisation, 1 - sum
+ * vacuum entry (permanent only).  Entries come back in the reference's dict insertion order:
+ *   keys [count][n_modes] uint8, vals [count].  backend: 0 = permanent, 1 = slos.
+ * Returns LWB_E_LIMIT if more than `cap` entries would be produced (count_out is still set). */
+enum { LWB_BACKEND_PERMANENT = 0, LWB_BACKEND_SLOS = 1 };
+int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state,
+              double threshold, int backend, int dtype, uint8_t* keys, double* vals, uint64_t cap,
+              uint64_t* count_out);
 
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */

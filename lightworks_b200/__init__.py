@@ -21,4 +21,14 @@ from ._lib import (  # noqa: F401
     slos_unrank,
 )
 
+from .backends import (  # noqa: E402, F401
+    Backend,
+    LazyDistribution,
+    PermanentBackend,
+    SLOSBackend,
+    install,
+    uninstall,
+)
+from .state import CompiledCircuitView, State  # noqa: E402, F401
+
 __version__ = "0.1.0"

@@ -14,7 +14,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblwb200.so")
+LIB_PATH = os.environ.get("LWB_LIB_PATH") or os.path.join(_HERE, "liblwb200.so")  # override: experiment builds
 
 LWB_C128, LWB_C64 = 0, 1
 LWB_E_ARG, LWB_E_PHOTONS, LWB_E_LIMIT, LWB_E_CUDA, LWB_E_NOMEM = -1, -2, -3, -4, -5
@@ -39,7 +39,7 @@ SIGNATURES = {
     "lwb_destroy": (_i, [_vp]),
     "lwb_last_error": (C.c_char_p, []),
     "lwb_version": (_i, []),
-    "lwb_set_stream": (_i, [_vp, _vp]),
+    "lwb_set_stream": (_i, [_vp, _vp, _i]),
     "lwb_synchronize": (_i, [_vp]),
     "lwb_device_info": (_i, [_vp, _pi, _pi, C.c_char_p, _i]),
     "lwb_set_tuning": (_i, [_i, _i, _i]),
@@ -59,6 +59,11 @@ SIGNATURES = {
     "lwb_perm_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _u64, _u64, _i, _vp]),
     "lwb_perm_single": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "lwb_perm_single_dev": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "lwb_slos_amplitudes": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "lwb_slos_amplitudes_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "lwb_slos_basis_probs": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "lwb_slos_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
+    "lwb_pdist": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _i, _vp, _vp, _u64, _pu64]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
 }
 
@@ -172,7 +177,12 @@ class Context:
         return self._h
 
     def set_stream(self, cuda_stream: int | None):
-        check(cdll().lwb_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        """Enqueue on a caller-owned stream (raw cudaStream_t; 0 = legacy default stream);
+        None restores the handle's own stream."""
+        if cuda_stream is None:
+            check(cdll().lwb_set_stream(self._h, C.c_void_p(0), 1))
+        else:
+            check(cdll().lwb_set_stream(self._h, C.c_void_p(cuda_stream), 0))
 
     def synchronize(self):
         check(cdll().lwb_synchronize(self._h))
@@ -241,6 +251,69 @@ class Context:
         check(cdll().lwb_perm_single(self._h, ptr(A), A.shape[0], dtype, slice_, n_slices, ptr(out)))
         return complex(out[0], out[1])
 
+
+BACKEND_PERMANENT, BACKEND_SLOS = 0, 1
+ORDER_FOCK, ORDER_SLOS = 0, 1
+
+
+def _slos_methods():
+    def _prep(U, in_state):  # noqa: N803
+        U = np.ascontiguousarray(U, dtype=np.complex128)  # noqa: N806
+        s = _u8(in_state)
+        if U.ndim != 2 or U.shape[0] != U.shape[1] or len(s) != U.shape[0]:
+            raise ValueError("unitary / state dimensions do not match")
+        return U, s, fock_count(U.shape[0], int(s.sum()))
+
+    def slos_amplitudes(self, U, in_state, order=ORDER_SLOS):  # noqa: N803
+        """SLOSBackend.calculate (slos.py:82-105) as an array: amplitudes of every output state."""
+        U, s, S = _prep(U, in_state)  # noqa: N806
+        out = np.zeros(S, dtype=np.complex128)
+        check(cdll().lwb_slos_amplitudes(self._h, ptr(U), U.shape[0], ptr(s), order, ptr(out)))
+        return out
+
+    def slos_basis_probs(self, U, in_state, order=ORDER_SLOS, out=None):  # noqa: N803
+        U, s, S = _prep(U, in_state)  # noqa: N806
+        if out is None:
+            out = np.zeros(S, dtype=np.float64)
+        check(cdll().lwb_slos_basis_probs(self._h, ptr(U), U.shape[0], ptr(s), order, ptr(out)))
+        return out
+
+    def slos_basis_probs_dev(self, d_U, m, in_state, d_probs, order=ORDER_SLOS):  # noqa: N803
+        s = _u8(in_state)
+        check(cdll().lwb_slos_basis_probs_dev(self._h, ptr(d_U), m, ptr(s), order, ptr(d_probs)))
+
+    def slos_amplitudes_dev(self, d_U, m, in_state, d_amps, order=ORDER_SLOS):  # noqa: N803
+        s = _u8(in_state)
+        check(cdll().lwb_slos_amplitudes_dev(self._h, ptr(d_U), m, ptr(s), order, ptr(d_amps)))
+
+    def pdist(self, U_full, n_modes, in_state, threshold=1e-9, backend=BACKEND_PERMANENT, dtype=LWB_C128):  # noqa: N803
+        """full_probability_distribution (permanent.py:116-163 / slos.py:43-80) as parallel arrays in the
+        reference's dict insertion order: (keys uint8[K, n_modes], vals float64[K])."""
+        from math import comb
+
+        U_full = np.ascontiguousarray(U_full, dtype=np.complex128)  # noqa: N806
+        s = _u8(in_state)
+        m_tot = U_full.shape[0]
+        if U_full.ndim != 2 or U_full.shape[1] != m_tot or len(s) != n_modes or n_modes > m_tot:
+            raise ValueError("unitary / state dimensions do not match")
+        n = int(s.sum())
+        if m_tot == n_modes:
+            cap = comb(m_tot + n - 1, n)
+        else:
+            cap = sum(comb(n_modes + k - 1, k) for k in range(n + 1)) + 1
+        keys = np.zeros((cap, n_modes), dtype=np.uint8)
+        vals = np.zeros(cap, dtype=np.float64)
+        count = C.c_uint64(0)
+        check(cdll().lwb_pdist(self._h, ptr(U_full), m_tot, n_modes, ptr(s), float(threshold), backend, dtype,
+                               ptr(keys), ptr(vals), cap, C.byref(count)))
+        k = int(count.value)
+        return keys[:k], vals[:k]
+
+    for f in (slos_amplitudes, slos_basis_probs, slos_basis_probs_dev, slos_amplitudes_dev, pdist):
+        setattr(Context, f.__name__, f)
+
+
+_slos_methods()
 
 _default_ctx: dict[int, Context] = {}
 

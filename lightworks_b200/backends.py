@@ -1,0 +1,349 @@
+"""
+Drop-in backends for the Lightworks emulator running on liblwb200.so (sm_100a).
+
+Mirrors the operator interface of the reference (same names, arguments and error behaviour):
+  lightworks/emulator/backends/fock_backend.py:43-124   FockBackend (the 4 overridable methods)
+  lightworks/emulator/backends/permanent.py:30-163      PermanentBackend
+  lightworks/emulator/backends/slos.py:28-105           SLOSBackend
+  lightworks/emulator/backends/backend.py:27-122        Backend (name -> class dispatch)
+
+Every numerical result comes from the CUDA library; there is no CPU fallback.  The classes work
+stand-alone (lists / numpy in, dict[State, float] out, with lightworks_b200.state.State keys) and,
+after `install()`, as subclasses of the reference's FockBackend inside an unmodified Lightworks SDK.
+"""
+from __future__ import annotations
+
+from collections.abc import Mapping
+
+import numpy as np
+
+from . import _lib
+from .state import CompiledCircuitView, State
+
+_DTYPES = {"complex128": _lib.LWB_C128, "complex64": _lib.LWB_C64, _lib.LWB_C128: _lib.LWB_C128, _lib.LWB_C64: _lib.LWB_C64}
+
+# Rebound to lightworks.State / settings by install(); module-level so the mixins stay import-light.
+_state_cls = State
+_settings = None
+
+
+def _threshold() -> float:
+    """settings.sampler_probability_threshold, read at call time (permanent.py:151, slos.py:74)."""
+    if _settings is not None:
+        return float(_settings.sampler_probability_threshold)
+    return 1e-9
+
+
+def _as_list(state) -> list[int]:
+    # the reference accepts State or list for both states (backend_test.py:145-151,172-178)
+    return list(state.s) if hasattr(state, "s") else [int(v) for v in state]
+
+
+class LazyDistribution(Mapping):
+    """dict[State, float] view over (keys uint8[K, m], vals[K]) that only builds State objects on
+    demand; iteration order = the reference's dict insertion order.  `.keys_array` / `.vals_array`
+    give the array-native form."""
+
+    def __init__(self, keys: np.ndarray, vals: np.ndarray, state_cls=None):
+        self.keys_array, self.vals_array = keys, vals
+        self._cls = state_cls or _state_cls
+        self._index = None
+
+    def _build(self):
+        if self._index is None:
+            self._index = {self._cls(k): i for i, k in enumerate(self.keys_array.tolist())}
+        return self._index
+
+    def __len__(self):
+        return len(self.vals_array)
+
+    def __iter__(self):
+        return iter(self._build())
+
+    def __getitem__(self, key):
+        return float(self.vals_array[self._build()[key]])
+
+    def to_dict(self) -> dict:
+        return {self._cls(k): float(v) for k, v in zip(self.keys_array.tolist(), self.vals_array)}
+
+
+class _B200Base:
+    """State shared by both backends: the device context and the arithmetic dtype."""
+
+    def __init__(self, device: int | None = None, dtype: str | int = "complex128"):
+        self._device = device
+        self._dtype = _DTYPES[dtype]
+        self._ctx = None
+
+    @property
+    def ctx(self) -> _lib.Context:
+        if self._ctx is None:
+            self._ctx = _lib.default_context(self._device)
+        return self._ctx
+
+    def _pdist_arrays(self, circuit, input_state, backend_id):
+        U = circuit.U_full  # noqa: N806
+        ins = _as_list(input_state)
+        if len(ins) != circuit.n_modes:
+            raise ValueError("input state length does not match the circuit")
+        return self.ctx.pdist(U, circuit.n_modes, ins, _threshold(), backend_id, self._dtype)
+
+
+class PermanentBackendMixin(_B200Base):
+    """PermanentBackend on the GPU: batched Glynn/Gray-code permanents (permanent.py:30-163)."""
+
+    @property
+    def name(self) -> str:
+        return "permanent"
+
+    @property
+    def compatible_tasks(self) -> tuple[str, ...]:
+        return ("Sampler", "Analyzer", "Simulator")
+
+    def state_generator(self, n_modes: int, n_photons: int) -> list[list[int]]:
+        """fock_basis(n_modes, n_photons), enumerated on the device (emulator/utils/state.py:22-35)."""
+        if n_photons == 0:
+            return [[0] * n_modes]
+        return self.ctx.fock_basis(n_modes, n_photons).tolist()
+
+    def state_generator_array(self, n_modes: int, n_photons: int) -> np.ndarray:
+        return self.ctx.fock_basis(n_modes, n_photons)
+
+    def probability_amplitude(self, unitary, input_state, output_state) -> complex:
+        """permanent.py:53-83"""
+        return complex(self.amplitude_matrix(unitary, [_as_list(input_state)], [_as_list(output_state)])[0, 0])
+
+    def probability(self, unitary, input_state, output_state) -> float:
+        """permanent.py:85-114: abs(amplitude) ** 2"""
+        return abs(self.probability_amplitude(unitary, input_state, output_state)) ** 2
+
+    def amplitude_matrix(self, unitary, inputs, outputs) -> np.ndarray:
+        """All <out|U|in> at once: the double loop of simulation/simulator.py:98-104."""
+        ins = np.array([_as_list(s) for s in inputs], dtype=np.uint8)
+        outs = np.array([_as_list(s) for s in outputs], dtype=np.uint8)
+        return self.ctx.perm_amplitudes(unitary, ins, outs, self._dtype, probs=False)
+
+    def probability_matrix(self, unitary, inputs, outputs) -> np.ndarray:
+        """All |<out|U|in>|^2 at once: the no-loss branch of simulation/analyzer.py:120-125."""
+        ins = np.array([_as_list(s) for s in inputs], dtype=np.uint8)
+        outs = np.array([_as_list(s) for s in outputs], dtype=np.uint8)
+        return self.ctx.perm_amplitudes(unitary, ins, outs, self._dtype, probs=True)
+
+    def full_probability_arrays(self, circuit, input_state):
+        """(keys, vals) of full_probability_distribution without building Python State objects."""
+        return self._pdist_arrays(circuit, input_state, _lib.BACKEND_PERMANENT)
+
+    def full_probability_distribution(self, circuit, input_state) -> dict:
+        """permanent.py:116-163"""
+        keys, vals = self._pdist_arrays(circuit, input_state, _lib.BACKEND_PERMANENT)
+        return {_state_cls(k): float(v) for k, v in zip(keys.tolist(), vals)}
+
+
+class SLOSBackendMixin(_B200Base):
+    """SLOSBackend on the GPU: layer-by-layer state-vector evolution (slos.py:28-138)."""
+
+    @property
+    def name(self) -> str:
+        return "slos"
+
+    @property
+    def compatible_tasks(self) -> tuple[str, ...]:
+        return ("Sampler",)
+
+    def full_probability_arrays(self, circuit, input_state):
+        return self._pdist_arrays(circuit, input_state, _lib.BACKEND_SLOS)
+
+    def full_probability_distribution(self, circuit, input_state) -> dict:
+        """slos.py:43-80"""
+        keys, vals = self._pdist_arrays(circuit, input_state, _lib.BACKEND_SLOS)
+        return {_state_cls(k): float(v) for k, v in zip(keys.tolist(), vals)}
+
+    def calculate_arrays(self, unitary, input_state):
+        """(states uint8[S, m], amplitudes complex128[S]) in the reference's dict insertion order."""
+        ins = _as_list(input_state)
+        U = np.ascontiguousarray(unitary, dtype=np.complex128)  # noqa: N806
+        m, n = U.shape[0], sum(ins)
+        amps = self.ctx.slos_amplitudes(U, ins, _lib.ORDER_SLOS)
+        states = np.array([_lib.slos_unrank(m, n, r) for r in range(len(amps))], dtype=np.uint8).reshape(len(amps), m)
+        return states, amps
+
+    def calculate(self, unitary, input_state) -> dict:
+        """slos.py:82-105: dict[tuple[int, ...], complex] in insertion order."""
+        states, amps = self.calculate_arrays(unitary, input_state)
+        return {tuple(k): complex(a) for k, a in zip(states.tolist(), amps)}
+
+
+# ---- stand-alone classes (no lightworks needed) ---------------------------------------------------
+class PermanentBackend(PermanentBackendMixin):
+    pass
+
+
+class SLOSBackend(SLOSBackendMixin):
+    pass
+
+
+class Backend:
+    """Stand-alone mirror of lightworks.emulator.Backend's selection behaviour (backend.py:42-45,
+    112-122) for the two hot-path methods; running Tasks needs the SDK, see install()."""
+
+    _backend_map = (("permanent", PermanentBackend), ("slos", SLOSBackend))
+
+    def __init__(self, backend: str) -> None:
+        backends = dict(self._backend_map)
+        if backend not in backends:
+            msg = f"Backend name not recognised, valid options are: {', '.join(backends.keys())}."
+            raise ValueError(msg)
+        self._backend = backends[backend]()
+
+    @property
+    def backend(self) -> str:
+        return self._backend.name
+
+    def __str__(self) -> str:
+        return self.backend
+
+
+# ---- integration with an importable Lightworks SDK -------------------------------------------------
+_installed = None
+
+
+def install(dtype: str = "complex128", device: int | None = None, patch_names: bool = True):
+    """Make `lightworks.emulator.Backend("permanent" | "slos")` run on the GPU.
+
+    Rebinds Backend._backend_map (a plain class attribute, backend.py:42-45) to subclasses of the
+    reference's FockBackend built here; the reference CPU backends stay reachable as
+    "permanent_cpu" / "slos_cpu".  With patch_names, `lightworks.emulator.backends.PermanentBackend`
+    / `.SLOSBackend` (the names user code imports) are rebound too; the reference classes stay in
+    their defining modules.  Returns (B200PermanentBackend, B200SLOSBackend).
+    """
+    global _installed, _state_cls, _settings
+    import lightworks as lw
+    from lightworks.emulator.backends.backend import Backend as LwBackend
+    from lightworks.emulator.backends.fock_backend import FockBackend
+    from lightworks.emulator.backends.permanent import PermanentBackend as RefPermanent
+    from lightworks.emulator.backends.slos import SLOSBackend as RefSLOS
+    from lightworks.emulator.simulation import AnalyzerRunner, SamplerRunner, SimulatorRunner  # noqa: F401
+    from lightworks.emulator.utils.exceptions import BackendError as LwBackendError
+    from lightworks.emulator.utils.sim import check_photon_numbers
+    from lightworks.sdk.results import SimulationResult
+    from lightworks.sdk.tasks import Analyzer, Sampler, Simulator
+    from lightworks.sdk.utils.exceptions import PhotonNumberError as LwPhotonNumberError
+    from lightworks.sdk.utils.heralding import add_heralds_to_state
+
+    if _installed is not None:
+        return _installed["classes"]
+    _state_cls = lw.State
+    _settings = lw.settings
+    _lib._exc["BackendError"] = LwBackendError
+    _lib._exc["PhotonNumberError"] = LwPhotonNumberError
+
+    class _BatchedAnalyzerRunner(AnalyzerRunner):
+        """AnalyzerRunner with `_get_probs` (simulation/analyzer.py:111-153) evaluated as ONE batched
+        device call per photon number instead of one Python call per (input, output) pair."""
+
+        def __init__(self, data, backend):
+            super().__init__(data, backend.probability, backend.state_generator)
+            self._b = backend
+
+        def _get_probs(self, full_inputs, full_outputs):
+            circuit = self.data.circuit
+            U, loss = circuit.U_full, circuit.loss_modes  # noqa: N806
+            probs = np.zeros((len(full_inputs), len(full_outputs)))
+            if not loss:  # analyzer.py:121-125
+                probs += self._b.probability_matrix(U, full_inputs, full_outputs)
+                return probs
+            n_in = sum(full_inputs[0])
+            by_loss: dict[int, list[int]] = {}
+            for j, outs in enumerate(full_outputs):
+                n_loss = n_in - sum(outs)
+                if n_loss < 0:  # analyzer.py:139-142
+                    raise LwPhotonNumberError("Output photon number larger than input number.")
+                by_loss.setdefault(n_loss, []).append(j)
+            for n_loss, cols in by_loss.items():
+                # every loss-mode completion of every output in this group (analyzer.py:144-151)
+                loss_states = self.state_generator(loss, n_loss)
+                expanded = [full_outputs[j] + ls for j in cols for ls in loss_states]
+                p = self._b.probability_matrix(U, full_inputs, expanded)
+                p = p.reshape(len(full_inputs), len(cols), len(loss_states))
+                for c, j in enumerate(cols):
+                    for q in range(len(loss_states)):  # same left-to-right accumulation as the reference
+                        probs[:, j] += p[:, c, q]
+            return probs
+
+    def _run_simulator(self, task):
+        """FockBackend.run_simulator + SimulatorRunner.run (fock_backend.py:53-58, simulator.py:58-111)
+        with the inputs x outputs double loop replaced by one batched device call."""
+        data = task._generate_task()
+        circuit = data.circuit
+        in_heralds, out_heralds = circuit.heralds.input, circuit.heralds.output
+        in_heralds_n, out_heralds_n = sum(in_heralds.values()), sum(out_heralds.values())
+        target_n = data.inputs[0].n_photons + in_heralds_n
+        check_photon_numbers(data.inputs, target_n - in_heralds_n)
+        if data.outputs is None:
+            outputs = [lw.State(s) for s in self.state_generator(circuit.input_modes, target_n - out_heralds_n)]
+        else:
+            check_photon_numbers(data.outputs, target_n - out_heralds_n)
+            outputs = data.outputs
+        pad = [0] * circuit.loss_modes
+        full_outputs = [add_heralds_to_state(o, out_heralds) + pad for o in outputs]
+        full_inputs = [add_heralds_to_state(i, in_heralds) + pad for i in data.inputs]
+        amplitudes = np.zeros((len(data.inputs), len(outputs)), dtype=complex)
+        amplitudes += self.amplitude_matrix(circuit.U_full, full_inputs, full_outputs)
+        return SimulationResult(amplitudes, "probability_amplitude", inputs=data.inputs, outputs=outputs)
+
+    def _run_analyzer(self, task):
+        return _BatchedAnalyzerRunner(task._generate_task(), self).run()
+
+    def _run(self, task):
+        # FockBackend.run is a multimethod object bound to the base implementations
+        # (fock_backend.py:49-68), so dispatch by task type here.
+        if isinstance(task, Simulator) and hasattr(self, "amplitude_matrix"):
+            return _run_simulator(self, task)
+        if isinstance(task, Analyzer) and hasattr(self, "probability_matrix"):
+            return _run_analyzer(self, task)
+        if isinstance(task, Sampler):
+            return FockBackend.run_sampler(self, task)  # inherits the pdist cache (fock_backend.py:67-87)
+        raise LwBackendError("Task not supported on current backend.")
+
+    class B200PermanentBackend(PermanentBackendMixin, FockBackend):
+        def __init__(self):
+            PermanentBackendMixin.__init__(self, device, dtype)
+
+        run = _run
+
+    class B200SLOSBackend(SLOSBackendMixin, FockBackend):
+        def __init__(self):
+            SLOSBackendMixin.__init__(self, device, dtype)
+
+        run = _run
+
+    import lightworks.emulator.backends as lw_backends_pkg
+
+    _installed = {"old_map": LwBackend._backend_map, "classes": (B200PermanentBackend, B200SLOSBackend),
+                  "Backend": LwBackend, "pkg": lw_backends_pkg, "patched": patch_names,
+                  "ref": (RefPermanent, RefSLOS)}
+    if patch_names:
+        lw_backends_pkg.PermanentBackend = B200PermanentBackend
+        lw_backends_pkg.SLOSBackend = B200SLOSBackend
+    LwBackend._backend_map = (
+        ("permanent", B200PermanentBackend),
+        ("slos", B200SLOSBackend),
+        ("permanent_cpu", RefPermanent),
+        ("slos_cpu", RefSLOS),
+    )
+    return _installed["classes"]
+
+
+def uninstall():
+    """Restore the reference's own backends."""
+    global _installed, _state_cls, _settings
+    if _installed is None:
+        return
+    _installed["Backend"]._backend_map = _installed["old_map"]
+    if _installed["patched"]:
+        _installed["pkg"].PermanentBackend, _installed["pkg"].SLOSBackend = _installed["ref"]
+    _installed = None
+    _state_cls = State
+    _settings = None
+    _lib._exc["BackendError"] = _lib.BackendError
+    _lib._exc["PhotonNumberError"] = _lib.PhotonNumberError

@@ -108,6 +108,18 @@ __host__ __device__ inline uint64_t lex_rank(const uint64_t* bin, const int* x, 
     return r;
 }
 
+// Successor in SLOS (lexicographic) order; returns false when x was the last state.
+__host__ __device__ inline bool lex_next(int* x, int n, int m) {
+    for (int i = n - 1; i >= 0; --i) {
+        if (x[i] < m - 1) {
+            const int v = x[i] + 1;
+            for (int q = i; q < n; ++q) x[q] = v;
+            return true;
+        }
+    }
+    return false;
+}
+
 __host__ __device__ inline void lex_unrank(const uint64_t* bin, uint64_t rank, int n, int m, int* x) {
     int prev = 0;
     for (int i = 0; i < n; ++i) {

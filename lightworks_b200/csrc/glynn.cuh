@@ -43,25 +43,27 @@ __device__ __forceinline__ void cmul(T& pr, T& pi, T ar, T ai) {
     pi = ni;
 }
 
-// product of w[0..N-1] with two interleaved chains (ILP 2, 8 live temporaries)
+// product of w[0..N-1] as LWB_CHAINS interleaved chains (ILP = LWB_CHAINS, 4*LWB_CHAINS live temporaries)
+#ifndef LWB_CHAINS
+#define LWB_CHAINS 2
+#endif
 template <int N, typename T>
 __device__ __forceinline__ void cprod(const T (&wr)[N], const T (&wi)[N], T& pr, T& pi) {
-    if constexpr (N < 4) {
-        pr = wr[0];
-        pi = wi[0];
+    constexpr int K = (N >= 2 * LWB_CHAINS) ? LWB_CHAINS : 1;
+    T cr[K], ci[K];
 #pragma unroll
-        for (int j = 1; j < N; ++j) cmul(pr, pi, wr[j], wi[j]);
-    } else {
-        constexpr int H = N / 2;
-        T ar = wr[0], ai = wi[0], br = wr[H], bi = wi[H];
+    for (int c = 0; c < K; ++c) {
+        constexpr int dummy = 0; (void)dummy;
+        const int lo = (N * c) / K, hi = (N * (c + 1)) / K;
+        cr[c] = wr[lo];
+        ci[c] = wi[lo];
 #pragma unroll
-        for (int j = 1; j < H; ++j) cmul(ar, ai, wr[j], wi[j]);
-#pragma unroll
-        for (int j = H + 1; j < N; ++j) cmul(br, bi, wr[j], wi[j]);
-        cmul(ar, ai, br, bi);
-        pr = ar;
-        pi = ai;
+        for (int j = lo + 1; j < hi; ++j) cmul(cr[c], ci[c], wr[j], wi[j]);
     }
+#pragma unroll
+    for (int c = 1; c < K; ++c) cmul(cr[0], ci[0], cr[c], ci[c]);
+    pr = cr[0];
+    pi = ci[0];
 }
 
 // Shared-memory row reads go through volatile inline PTX: the row table is loop-invariant, and

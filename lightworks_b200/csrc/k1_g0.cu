@@ -10,12 +10,13 @@ static const K1Variant table[] = {
     LWB_K1_ENTRY(5, 0),
     LWB_K1_ENTRY(6, 0),
     LWB_K1_ENTRY(7, 1),
-    LWB_K1_ENTRY(8, 2),
+    LWB_K1_ENTRY(8, 3),
     LWB_K1_ENTRY(6, 1),
     LWB_K1_ENTRY(7, 0),
     LWB_K1_ENTRY(7, 2),
     LWB_K1_ENTRY(8, 1),
-    LWB_K1_ENTRY(8, 3),
+    LWB_K1_ENTRY(8, 2),
+    LWB_K1_ENTRY(8, 4),
 };
 const K1Variant* k1_g0_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -4,13 +4,15 @@
 namespace lwb {
 static const K1Variant table[] = {
     LWB_K1_ENTRY(9, 3),
-    LWB_K1_ENTRY(10, 4),
-    LWB_K1_ENTRY(11, 5),
+    LWB_K1_ENTRY(10, 3),
+    LWB_K1_ENTRY(11, 4),
     LWB_K1_ENTRY(9, 2),
     LWB_K1_ENTRY(9, 4),
-    LWB_K1_ENTRY(10, 3),
+    LWB_K1_ENTRY(10, 2),
+    LWB_K1_ENTRY(10, 4),
     LWB_K1_ENTRY(10, 5),
-    LWB_K1_ENTRY(11, 4),
+    LWB_K1_ENTRY(11, 3),
+    LWB_K1_ENTRY(11, 5),
 };
 const K1Variant* k1_g1_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

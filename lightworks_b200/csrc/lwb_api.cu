@@ -14,6 +14,7 @@
 #include "fock.cuh"
 #include "misc_kernels.cuh"
 #include "perm_kernels.cuh"
+#include "slos_kernels.cuh"
 #include "variants.h"
 
 using namespace lwb;
@@ -51,7 +52,7 @@ struct lwb_context {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     uint64_t* d_bin = nullptr;
-    Buf bU, bIn, bOut, bRes, bPart, bTmp;
+    Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall;
     uint64_t launches = 0;
     std::mutex mu;
 };
@@ -152,7 +153,8 @@ int lwb_destroy(lwb_handle h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    for (Buf* b : {&h->bU, &h->bIn, &h->bOut, &h->bRes, &h->bPart, &h->bTmp})
+    for (Buf* b : {&h->bU, &h->bIn, &h->bOut, &h->bRes, &h->bPart, &h->bTmp, &h->bLayerA, &h->bLayerB, &h->bProbs,
+                   &h->bMarg, &h->bFirst, &h->bSmall})
         if (b->p) cudaFree(b->p);
     if (h->d_bin) cudaFree(h->d_bin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -160,9 +162,9 @@ int lwb_destroy(lwb_handle h) {
     return 0;
 }
 
-int lwb_set_stream(lwb_handle h, void* s) {
+int lwb_set_stream(lwb_handle h, void* s, int use_own) {
     if (!h) return fail(LWB_E_ARG, "null handle");
-    h->stream = s ? (cudaStream_t)s : h->own_stream;
+    h->stream = use_own ? h->own_stream : (cudaStream_t)s;  // s == NULL is the legacy default stream
     return 0;
 }
 
@@ -501,6 +503,261 @@ int lwb_fp64_peak(lwb_handle h, double* flops_per_s) {
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     *flops_per_s = best;
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- SLOS ----------------------------------------------------------------------------------------
+template <typename Args, typename K4, typename K8, typename K12, typename K16, typename K24, typename K40>
+static int launch_kmax(lwb_handle h, int n, uint64_t threads_needed, size_t smem, const Args& a, K4 k4, K8 k8, K12 k12,
+                       K16 k16, K24 k24, K40 k40) {
+    const unsigned grid = (unsigned)((threads_needed + SLOS_THREADS - 1) / SLOS_THREADS);
+    if (grid == 0) return 0;
+#define LWB_GO(fn)                                                                                   \
+    do {                                                                                             \
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fn<<<grid, SLOS_THREADS, smem, h->stream>>>(a);                                              \
+    } while (0)
+    if (n <= 4) LWB_GO(k4);
+    else if (n <= 8) LWB_GO(k8);
+    else if (n <= 12) LWB_GO(k12);
+    else if (n <= 16) LWB_GO(k16);
+    else if (n <= 24) LWB_GO(k24);
+    else LWB_GO(k40);
+#undef LWB_GO
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Runs every SLOS layer; on return *final points at the device layer holding the S(m,n) amplitudes in
+// colex order (one of the handle's two layer buffers).
+static int slos_layers(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int n, const double2** final) {
+    const uint64_t* hb = host_bin();
+    const uint64_t S = binom(hb, m + n - 1, n);
+    const uint64_t Sp = n >= 1 ? binom(hb, m + n - 2, n - 1) : 1;
+    // ping-pong so that the last layer lands in bLayerA
+    CK(ensure(h, h->bLayerA, std::max<uint64_t>(S, 1) * 16));
+    CK(ensure(h, h->bLayerB, std::max<uint64_t>(Sp, 1) * 16));
+    CK(ensure(h, h->bSmall, 4096));
+    double vf = 1.0;  // vector_factorial, slos.py:126-128
+    int modes[LWB_MAX_PHOTONS + 1];
+    int c = 0;
+    for (int i = 0; i < m; ++i)
+        for (int k = 0; k < in_state[i]; ++k) { modes[c++] = i; vf *= (double)(k + 1); }
+    double host_small[64 + 2];
+    host_small[0] = 1.0 / sqrt(vf);  // 1 / np.sqrt(vector_factorial), slos.py:92
+    host_small[1] = 0.0;
+    for (int k = 0; k <= n; ++k) host_small[2 + k] = pow((double)k, 0.5);  // key[mode] ** 0.5, slos.py:121
+    CU(cudaMemcpyAsync(h->bSmall.p, host_small, sizeof(double) * (size_t)(n + 3), cudaMemcpyHostToDevice, h->stream));
+    // layer 0 goes into the buffer that makes layer n end in A
+    double2* bufs[2] = {(double2*)h->bLayerA.p, (double2*)h->bLayerB.p};
+    int cur = (n % 2 == 0) ? 0 : 1;
+    CU(cudaMemcpyAsync(bufs[cur], h->bSmall.p, 16, cudaMemcpyDeviceToDevice, h->stream));
+    for (int k = 1; k <= n; ++k) {
+        SlosLayerArgs a;
+        a.bin = h->d_bin; a.m = m; a.k = k; a.S = binom(hb, m + k - 1, k);
+        a.parent = bufs[cur]; a.child = bufs[cur ^ 1]; a.U = (const double2*)d_U; a.in_mode = modes[k - 1];
+        a.sqrt_tab = (const double*)h->bSmall.p + 2;
+        const size_t smem = (size_t)(m + k) * (k + 1) * 8 + (size_t)m * 16 + (size_t)(k + 1) * 8;
+        CK(launch_kmax(h, k, a.S, smem, a, slos_layer_kernel<4>, slos_layer_kernel<8>, slos_layer_kernel<12>,
+                       slos_layer_kernel<16>, slos_layer_kernel<24>, slos_layer_kernel<40>));
+        cur ^= 1;
+    }
+    *final = bufs[cur];
+    return 0;
+}
+
+static int slos_check(int m, const uint8_t* in_state, int* n_out) {
+    if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
+    int n = 0;
+    for (int i = 0; i < m; ++i) n += in_state[i];
+    CK(check_mn(m, n));
+    *n_out = n;
+    return 0;
+}
+
+// out_mode: 0 complex amplitudes, 1 probabilities
+static int slos_run_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order, int out_mode,
+                        double* d_out) {
+    int n = 0;
+    CK(slos_check(m, in_state, &n));
+    if (order != 0 && order != 1) return fail(LWB_E_ARG, "order %d", order);
+    CU(cudaSetDevice(h->device));
+    const uint64_t S = binom(host_bin(), m + n - 1, n);
+    const double2* fin = nullptr;
+    CK(slos_layers(h, d_U, m, in_state, n, &fin));
+    if (order == 0) {
+        if (out_mode == 0) CU(cudaMemcpyAsync(d_out, fin, S * 16, cudaMemcpyDeviceToDevice, h->stream));
+        else {
+            abs2_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(fin, S, d_out);
+            h->launches++;
+            CU(cudaGetLastError());
+        }
+    } else {
+        ReorderArgs ra{h->d_bin, m, n, S, (const double*)fin, d_out, out_mode};
+        CK(launch_kmax(h, n, S, 0, ra, reorder_lex_kernel<4>, reorder_lex_kernel<8>, reorder_lex_kernel<12>,
+                       reorder_lex_kernel<16>, reorder_lex_kernel<24>, reorder_lex_kernel<40>));
+    }
+    return 0;
+}
+
+static int slos_run_host(lwb_handle h, const double* U, int m, const uint8_t* in_state, int order, int out_mode,
+                         double* out) {
+    if (!h || !U || !in_state || !out) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    int n = 0;
+    CK(slos_check(m, in_state, &n));
+    CU(cudaSetDevice(h->device));
+    const uint64_t S = binom(host_bin(), m + n - 1, n);
+    const size_t per = out_mode == 0 ? 16 : 8;
+    CK(ensure(h, h->bU, (size_t)m * m * 16));
+    CK(ensure(h, h->bRes, S * per));
+    CU(cudaMemcpyAsync(h->bU.p, U, (size_t)m * m * 16, cudaMemcpyHostToDevice, h->stream));
+    CK(slos_run_dev(h, (const double*)h->bU.p, m, in_state, order, out_mode, (double*)h->bRes.p));
+    CU(cudaMemcpyAsync(out, h->bRes.p, S * per, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" {
+
+int lwb_slos_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order, double* d_amps) {
+    if (!h || !in_state) return fail(LWB_E_ARG, "null argument");
+    return slos_run_dev(h, d_U, m, in_state, order, 0, d_amps);
+}
+int lwb_slos_amplitudes(lwb_handle h, const double* U, int m, const uint8_t* in_state, int order, double* amps) {
+    return slos_run_host(h, U, m, in_state, order, 0, amps);
+}
+int lwb_slos_basis_probs_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order, double* d_probs) {
+    if (!h || !in_state) return fail(LWB_E_ARG, "null argument");
+    return slos_run_dev(h, d_U, m, in_state, order, 1, d_probs);
+}
+int lwb_slos_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in_state, int order, double* probs) {
+    return slos_run_host(h, U, m, in_state, order, 1, probs);
+}
+
+// ---- full distribution -----------------------------------------------------------------------------
+int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state, double threshold,
+              int backend, int dtype, uint8_t* keys, double* vals, uint64_t cap, uint64_t* count_out) {
+    if (!h || !U_full || !in_state || !keys || !vals || !count_out) return fail(LWB_E_ARG, "null argument");
+    if (backend != LWB_BACKEND_PERMANENT && backend != LWB_BACKEND_SLOS) return fail(LWB_E_ARG, "backend %d", backend);
+    if (n_modes < 1 || n_modes > m_tot) return fail(LWB_E_ARG, "n_modes=%d outside [1,%d]", n_modes, m_tot);
+    if (m_tot > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m_tot, LWB_MAX_MODES);
+    std::lock_guard<std::mutex> lk(h->mu);
+    const uint64_t* hb = host_bin();
+    const int loss = m_tot - n_modes;
+    int n = 0;
+    for (int i = 0; i < n_modes; ++i) n += in_state[i];
+    *count_out = 0;
+    if (n == 0) {  // permanent.py:137-138, slos.py:64-65
+        *count_out = 1;
+        if (cap < 1) return fail(LWB_E_LIMIT, "capacity");
+        memset(keys, 0, (size_t)n_modes);
+        vals[0] = 1.0;
+        return 0;
+    }
+    CK(check_mn(m_tot, n));
+    if (backend == LWB_BACKEND_PERMANENT && n > LWB_K1_MAX_N)
+        return fail(LWB_E_LIMIT, "permanent backend supports up to %d photons (got %d)", LWB_K1_MAX_N, n);
+    CU(cudaSetDevice(h->device));
+    const uint64_t S = binom(hb, m_tot + n - 1, n);
+    uint8_t full_in[LWB_MAX_MODES];
+    memset(full_in, 0, sizeof full_in);
+    memcpy(full_in, in_state, (size_t)n_modes);  // permanent.py:142-143, slos.py:69-70
+
+    // 1. per-full-state probabilities on the device, colex order
+    CK(ensure(h, h->bU, (size_t)m_tot * m_tot * 16));
+    CK(ensure(h, h->bProbs, S * 8));
+    CU(cudaMemcpyAsync(h->bU.p, U_full, (size_t)m_tot * m_tot * 16, cudaMemcpyHostToDevice, h->stream));
+    const int order = backend == LWB_BACKEND_SLOS ? 1 : 0;
+    if (backend == LWB_BACKEND_PERMANENT) {
+        CK(ensure(h, h->bIn, (size_t)m_tot));
+        CU(cudaMemcpyAsync(h->bIn.p, full_in, (size_t)m_tot, cudaMemcpyHostToDevice, h->stream));
+        CK(launch_states(h, (const double*)h->bU.p, m_tot, (const uint8_t*)h->bIn.p, 1, nullptr, 0, S, n, dtype, 1,
+                         (double*)h->bProbs.p));
+    } else {
+        // without loss modes the SLOS order is produced directly; with loss the marginaliser wants colex
+        CK(slos_run_dev(h, (const double*)h->bU.p, m_tot, full_in, loss == 0 ? 1 : 0, 1, (double*)h->bProbs.p));
+    }
+
+    if (loss == 0) {
+        // 2a. no loss modes: every full state is its own key; filter p > threshold in enumeration order
+        std::vector<double> p(S);
+        CU(cudaMemcpyAsync(p.data(), h->bProbs.p, S * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        int x[LWB_MAX_PHOTONS + 1];
+        for (int i = 0; i < n; ++i) x[i] = 0;  // first state in both orders: all photons in mode 0
+        uint64_t cnt = 0;
+        for (uint64_t r = 0; r < S; ++r) {
+            if (p[r] > threshold) {
+                if (cnt < cap) {
+                    modes_to_state(x, n, n_modes, keys + cnt * (uint64_t)n_modes);
+                    vals[cnt] = p[r];
+                }
+                ++cnt;
+            }
+            if (order == 0) colex_next(x, n, m_tot);
+            else lex_next(x, n, m_tot);
+        }
+        *count_out = cnt;
+        if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
+                                   (unsigned long long)cap);
+        return 0;
+    }
+
+    // 2b. loss modes: marginalise on the device, order the keys by first appearance on the host
+    const int k_min = backend == LWB_BACKEND_PERMANENT ? 1 : 0;  // permanent.py:148-149 skips zero-real-photon states
+    uint64_t key_off[LWB_MAX_PHOTONS + 3];
+    uint64_t nk = 0;
+    for (int kk = 0; kk <= n + 1; ++kk) {
+        key_off[kk] = nk;
+        if (kk >= k_min && kk <= n) nk += binom(hb, n_modes + kk - 1, kk);
+    }
+    CK(ensure(h, h->bMarg, nk * 8));
+    CK(ensure(h, h->bFirst, nk * 8));
+    CK(ensure(h, h->bSmall, 4096));
+    CU(cudaMemcpyAsync((char*)h->bSmall.p + 2048, key_off, sizeof(uint64_t) * (size_t)(n + 2), cudaMemcpyHostToDevice, h->stream));
+    MargArgs ma;
+    ma.bin = h->d_bin; ma.m_tot = m_tot; ma.n_modes = n_modes; ma.n = n; ma.k_min = k_min;
+    ma.key_off = (const uint64_t*)((char*)h->bSmall.p + 2048); ma.n_keys = nk; ma.probs = (const double*)h->bProbs.p;
+    ma.threshold = threshold; ma.order = order; ma.marg = (double*)h->bMarg.p; ma.first_pos = (uint64_t*)h->bFirst.p;
+    CK(launch_kmax(h, n, nk, 0, ma, marginalise_kernel<4>, marginalise_kernel<8>, marginalise_kernel<12>,
+                   marginalise_kernel<16>, marginalise_kernel<24>, marginalise_kernel<40>));
+    std::vector<double> marg(nk);
+    std::vector<uint64_t> first(nk);
+    CU(cudaMemcpyAsync(marg.data(), h->bMarg.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(first.data(), h->bFirst.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<uint64_t> idx;
+    for (uint64_t k = 0; k < nk; ++k)
+        if (first[k] != UINT64_MAX) idx.push_back(k);
+    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return first[a] < first[b]; });
+    uint64_t cnt = 0;
+    double total = 0.0;  // sum(pdist.values()) in dict order, permanent.py:159
+    for (uint64_t k : idx) {
+        int kk = k_min;
+        while (kk < n && k >= key_off[kk + 1]) ++kk;
+        if (cnt < cap) {
+            int x[LWB_MAX_PHOTONS + 1];
+            colex_unrank(hb, k - key_off[kk], kk, n_modes, x);
+            modes_to_state(x, kk, n_modes, keys + cnt * (uint64_t)n_modes);
+            vals[cnt] = marg[k];
+        }
+        total += marg[k];
+        ++cnt;
+    }
+    if (backend == LWB_BACKEND_PERMANENT && total < 1.0) {  // permanent.py:160-161 (loss_modes > 0 here)
+        if (cnt < cap) {
+            memset(keys + cnt * (uint64_t)n_modes, 0, (size_t)n_modes);
+            vals[cnt] = 1.0 - total;
+        }
+        ++cnt;
+    }
+    *count_out = cnt;
+    if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
+                               (unsigned long long)cap);
     return 0;
 }
 

@@ -14,13 +14,22 @@
 namespace lwb {
 
 constexpr int K1_THREADS = 256;
+#ifndef LWB_U
+#define LWB_U 3   /* K1: statically unrolled low Gray bits (measured best of 1,2,3 on B200) */
+#endif
+#ifndef LWB_U2
+#define LWB_U2 2  /* K2 */
+#endif
+#ifndef LWB_MINB
+#define LWB_MINB 1
+#endif
 
 // Work split shared by all kernels: LOG_L lanes-per-permanent exponent and chunk bits.
 template <int N, int LOG_L>
 struct K1Shape {
     static constexpr int L = 1 << LOG_L;
     static constexpr int C = N - 1 - LOG_L;          // steps per lane = 2^C
-    static constexpr int U = C < 2 ? C : 2;          // statically unrolled low bits
+    static constexpr int U = C < LWB_U ? C : LWB_U;  // statically unrolled low bits
     static constexpr int GPB = K1_THREADS / L;       // groups (permanents in flight) per block
 };
 
@@ -43,7 +52,7 @@ __device__ __forceinline__ T group_sum(T v, int log_l) {
 }
 
 template <int N, int LOG_L, typename T>
-__global__ void __launch_bounds__(K1_THREADS) perm_states_kernel(PermStatesArgs a) {
+__global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermStatesArgs a) {
     using S = K1Shape<N, LOG_L>;
     using V = typename vec2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -172,7 +181,7 @@ struct PermMatricesArgs {
 };
 
 template <int N, int LOG_L, typename T>
-__global__ void __launch_bounds__(K1_THREADS) perm_matrices_kernel(PermMatricesArgs a) {
+__global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_matrices_kernel(PermMatricesArgs a) {
     using S = K1Shape<N, LOG_L>;
     using V = typename vec2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -226,11 +235,11 @@ template <int N>
 struct K2Shape {
     static constexpr int C0 = N - 16;
     static constexpr int C = C0 < 4 ? (N - 1 < 4 ? N - 1 : 4) : (C0 > 10 ? 10 : C0);
-    static constexpr int U = C < 2 ? C : 2;
+    static constexpr int U = C < LWB_U2 ? C : LWB_U2;
 };
 
 template <int N, typename T>
-__global__ void __launch_bounds__(K1_THREADS) perm_single_kernel(PermSingleArgs a) {
+__global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermSingleArgs a) {
     using S = K2Shape<N>;
     using V = typename vec2<T>::type;
     __shared__ __align__(16) V Ms[N * N];

@@ -23,7 +23,19 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("LW_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _find_reference() -> str:
+    """/root/reference in the build container; on the GPU box the pip-installed copy under
+    baseline/_ref (git-ignored, created by __graft_entry__.build(); it travels with gpurun)."""
+    for cand in (os.environ.get("LW_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if cand and os.path.isdir(os.path.join(cand, "lightworks")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available() -> bool:

@@ -10,7 +10,8 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "reference: needs /root/reference (build container only)")
+    config.addinivalue_line("markers", "reference: needs an importable reference (/root/reference or baseline/_ref)")
+    config.addinivalue_line("markers", "flaky: rerun marker of the reference's own tests (pytest-rerunfailures absent)")
 
 
 def _has_gpu() -> bool:
@@ -24,7 +25,9 @@ def _has_gpu() -> bool:
 
 def pytest_collection_modifyitems(config, items):
     has_gpu = _has_gpu()
-    has_ref = os.path.isdir("/root/reference/lightworks")
+    from oracle import refshim
+
+    has_ref = refshim.reference_available()
     for item in items:
         if "gpu" in item.keywords and not has_gpu:
             item.add_marker(pytest.mark.skip(reason="no CUDA device in this container"))

@@ -1,0 +1,106 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/lwb200.h declares, the
+host-only Fock indexing is bit-exact with the reference order, and the shard arithmetic is sound."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lightworks_b200 as lb
+from lightworks_b200 import _lib, sharding
+from oracle import oracle as O  # noqa: N812
+from tests.golden_util import golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "lwb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lwb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.cdll()
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lwb200.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == names
+    assert lib.lwb_version() >= 100
+
+
+def test_compute_calls_fail_loudly_without_gpu():
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(lb.BackendError):
+        _lib.Context(0)
+    with pytest.raises(lb.BackendError):  # no silent CPU fallback in the product path
+        lb.PermanentBackend().probability_amplitude(np.eye(2), [1, 0], [1, 0])
+
+
+@pytest.mark.parametrize("rec", golden().of_kind("fock"), ids=lambda r: f"m{r['m']}n{r['n']}")
+def test_host_rank_unrank_bit_exact(rec):
+    ref = golden().arr(rec["basis"])
+    m, n = rec["m"], rec["n"]
+    assert lb.fock_count(m, n) == len(ref)
+    step = max(1, len(ref) // 400)
+    for r in list(range(0, len(ref), step)) + [len(ref) - 1]:
+        assert np.array_equal(lb.fock_unrank(m, n, r), ref[r])
+        assert lb.fock_rank(ref[r]) == r
+
+
+def test_slos_order_matches_reference_dict_order():
+    for rec in golden().of_kind("slos"):
+        keys = golden().arr(rec["keys"])
+        m, n = keys.shape[1], int(keys[0].sum())
+        step = max(1, len(keys) // 300)
+        for r in range(0, len(keys), step):
+            assert np.array_equal(lb.slos_unrank(m, n, r), keys[r])
+            assert lb.slos_rank(keys[r]) == r
+
+
+def test_rank_formulas_at_scale():
+    # C3 (24 modes, 10 photons): rank <-> unrank round trip at random ranks and the extremes
+    S = lb.fock_count(24, 10)  # noqa: N806
+    assert S == 92561040 and lb.fock_count(40, 20) == 2794563003870330
+    rng = np.random.default_rng(0)
+    for r in [0, 1, S - 1, *rng.integers(0, S, 200).tolist()]:
+        s = lb.fock_unrank(24, 10, int(r))
+        assert s.sum() == 10 and lb.fock_rank(s) == r
+        t = lb.slos_unrank(24, 10, int(r))
+        assert t.sum() == 10 and lb.slos_rank(t) == r
+    assert lb.fock_unrank(24, 10, 0).tolist() == [10] + [0] * 23
+    assert lb.fock_unrank(24, 10, S - 1).tolist() == [0] * 23 + [10]
+    with pytest.raises(ValueError):
+        lb.fock_unrank(24, 10, S)
+    with pytest.raises(ValueError):
+        lb.fock_count(300, 3)
+    with pytest.raises(ValueError):
+        lb.fock_count(60, 28)  # C(87,28) does not fit 64-bit ranks: refused, not wrapped
+
+
+def test_shard_ranges_partition_exactly():
+    for S in [1, 7, 56, 12376, 92561040]:  # noqa: N806
+        for world in [1, 2, 3, 4, 8]:
+            rs = [sharding.rank_range(S, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == S
+            assert all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_state_mirror_matches_reference_semantics():
+    s = lb.State([1, 0, 2])
+    assert str(s) == "|1,0,2>" and s.n_photons == 3 and s.n_modes == 3
+    assert s == lb.State((1, 0, 2)) and hash(s) == hash(lb.State([1, 0, 2]))
+    assert (s + lb.State([0])).s == [1, 0, 2, 0] and s[:2] == lb.State([1, 0]) and s[2] == 2
+    c = lb.CompiledCircuitView(np.eye(5), n_modes=3)
+    assert c.loss_modes == 2
+    assert O.fock_count(5, 2) == lb.fock_count(5, 2)

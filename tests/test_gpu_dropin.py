@@ -1,0 +1,126 @@
+"""
+Drop-in tests: the UNMODIFIED Lightworks SDK (tasks, circuits, source/detector models, result types)
+running on the B200 backends through `lightworks_b200.install()`, compared with the reference's own
+CPU backends in the same process.  Needs a GPU and an importable reference (baseline/_ref on the GPU
+box, /root/reference in the build container); skipped otherwise.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu, pytest.mark.reference]
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lw():
+    from oracle import refshim
+
+    lightworks = refshim.import_lightworks()
+    import lightworks_b200
+
+    lightworks_b200.install()
+    yield lightworks
+    lightworks_b200.uninstall()
+
+
+def _close(a, b, rel=1e-10, abs_=1e-15):
+    return np.all(np.abs(np.asarray(a) - np.asarray(b)) <= rel * np.abs(np.asarray(b)) + abs_)
+
+
+def test_backend_selection(lw):
+    from lightworks.emulator import Backend
+
+    assert str(Backend("permanent")) == "permanent"
+    assert type(Backend("permanent")._backend).__name__ == "B200PermanentBackend"
+    assert type(Backend("slos")._backend).__name__ == "B200SLOSBackend"
+    with pytest.raises(ValueError):
+        Backend("not_a_backend")
+    from lightworks.emulator import BackendError
+
+    with pytest.raises(BackendError):  # slos is Sampler-only (backend_test.py:41-48)
+        Backend("slos").run(lw.Simulator(lw.Unitary(lw.random_unitary(4)), lw.State([1, 0, 1, 0])))
+
+
+@pytest.mark.parametrize("m,n,seed", [(6, 3, 1), (12, 6, 2)])
+def test_simulator_c1_c2(lw, m, n, seed):
+    from lightworks.emulator import Backend
+
+    task = lw.Simulator(lw.Unitary(lw.random_unitary(m, seed=seed)), lw.State([1] * n + [0] * (m - n)))
+    got, ref = Backend("permanent").run(task), Backend("permanent_cpu").run(task)
+    assert got.outputs == ref.outputs and got.inputs == ref.inputs
+    assert _close(got.array, ref.array)
+
+
+def test_analyzer_c2_and_lossy_heralded(lw):
+    from lightworks.emulator import Backend
+
+    task = lw.Analyzer(lw.Unitary(lw.random_unitary(12, seed=2)), lw.State([1] * 6 + [0] * 6))
+    got, ref = Backend("permanent").run(task), Backend("permanent_cpu").run(task)
+    assert got.outputs == ref.outputs
+    assert _close(got.array, ref.array)
+    assert got.performance == pytest.approx(ref.performance, rel=1e-10)
+    # lossy + herald + post-selection: loss-mode summation path (analyzer.py:136-151)
+    circ = lw.PhotonicCircuit(5)
+    circ.add(lw.Unitary(lw.random_unitary(5, seed=5)))
+    for i in range(5):
+        circ.loss(i, 0.15 + 0.05 * i)
+    circ.herald(4, 0)
+    an = lw.Analyzer(circ, [lw.State([1, 1, 0, 1]), lw.State([0, 1, 1, 1])])
+    an.post_selection = lambda s: s[0] <= 1
+    got, ref = Backend("permanent").run(an), Backend("permanent_cpu").run(an)
+    assert got.outputs == ref.outputs
+    assert _close(got.array, ref.array, 1e-10, 1e-16)
+    assert got.performance == pytest.approx(ref.performance, rel=1e-10)
+
+
+@pytest.mark.parametrize("name", ["permanent", "slos"])
+def test_sampler_distribution_and_samples(lw, name):
+    from lightworks.emulator import Backend, Detector, Source
+
+    circ = lw.PhotonicCircuit(6)
+    circ.add(lw.Unitary(lw.random_unitary(6, seed=8)))
+    for i in range(6):
+        circ.loss(i, 0.1)
+    src = Source(purity=0.95, brightness=0.9, indistinguishability=0.9)
+    mk = lambda: lw.Sampler(circ, lw.State([1, 0, 1, 0, 1, 0]), 2000, source=src,  # noqa: E731
+                            detector=Detector(efficiency=0.9), random_seed=7)
+    t1, t2 = mk(), mk()
+    r1 = Backend(name).run(t1)
+    r2 = Backend(name + "_cpu").run(t2)
+    d1, d2 = dict(t1.probability_distribution), dict(t2.probability_distribution)
+    assert list(d1) == list(d2)  # same states in the same order
+    vac = lw.State([0] * 6)
+    for k in d2:
+        if k == vac:
+            assert d1[k] == pytest.approx(d2[k], abs=1e-12)
+        else:
+            assert d1[k] == pytest.approx(d2[k], rel=1e-9, abs=1e-16)
+    # same seed, same ordered distribution -> the drawn samples agree unless a cumulative-sum edge moves
+    c1, c2 = dict(r1), dict(r2)
+    assert sum(c1.values()) == sum(c2.values())
+    common = sum(min(c1.get(k, 0), c2.get(k, 0)) for k in set(c1) | set(c2))
+    assert common >= 0.99 * sum(c2.values())
+
+
+def test_sampler_cache_is_inherited(lw):
+    # fock_backend.py:67-87 / backend_test.py:255-267
+    from lightworks.emulator import Backend
+
+    b = Backend("permanent")
+    s = lw.Sampler(lw.Unitary(lw.random_unitary(4, seed=3)), lw.State([1, 0, 1, 0]), 100)
+    b.run(s)
+    assert b._backend._check_cache(s._generate_task()) is not None
+
+
+def test_reference_emulator_suite_runs_on_b200():
+    """The reference's own tests/emulator suite with Backend("permanent"/"slos"), PermanentBackend and
+    SLOSBackend redirected to the B200 classes (SURVEY.md section 8d 'correctness gates')."""
+    r = subprocess.run([sys.executable, "-m", "oracle.run_reference_tests", "--b200", "-x"], cwd=ROOT,
+                       capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
