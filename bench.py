@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""
+bench.py -- headline benchmark of the Lightworks emulator probability hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the largest configuration that fits one GPU; SURVEY.md 8d "C3"):
+    Sampler / Permanent backend, 24-mode Haar-random unitary (scipy unitary_group, seed 3), input
+    |1^10, 0^14>, ALL 92 561 040 output-state probabilities |Perm(U_{S,T})|^2 / (prod s! prod t!).
+One step = one pass over that distribution.  With N GPUs the output Fock states are sharded by
+contiguous rank ranges of the reference's fock_basis order (strong scaling: total work fixed); the
+step then ends with the NCCL all-gather of the probability shards and the scalar all-reduce of their
+sum (the normalisation check), as BASELINE.json's north_star describes.
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+M, N_PH, SEED = 24, 10, 3
+WORKLOAD = ("C3: Sampler/Permanent backend, 24-mode Haar unitary (seed 3), 10 photons |1^10,0^14>, "
+            "all 92,561,040 output-state probabilities")
+METRIC = "output-state probabilities/sec (complex128 10x10 permanents, full distribution)"
+UNIT = "probabilities/s"
+
+
+def flops_per_perm(n: int) -> float:
+    """Algorithmic FP64 flops of one n x n complex128 Glynn/Gray permanent."""
+    return 2.0 ** (n - 1) * (8 * n - 4)
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows: list[list[str]] = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_baseline(U, ins, sample: int, threads: int) -> dict:  # noqa: N803
+    """The oracle's C restatement of the reference loop (permanent.py:145-150), all host threads, on a
+    bounded prefix of the same workload."""
+    from oracle import oracle as O  # noqa: N812  (bench.py's cpu_baseline leg may execute oracle/)
+
+    O.basis_probabilities(U, ins, 0, 64, threads=threads)  # warm
+    t0 = time.perf_counter()
+    O.basis_probabilities(U, ins, 0, sample, threads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"first {sample} of 92561040 output states in fock_basis order, oracle/lw_oracle.c "
+                      f"(restated thewalrus perm_bbfg), {threads} pthreads, {dt:.2f} s"}
+
+
+def run_reference_arm(args) -> int:
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import oracle as O  # noqa: N812
+    from oracle import refshim
+
+    U = O.random_unitary(M, SEED)  # noqa: N806
+    ins = [1] * N_PH + [0] * (M - N_PH)
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "c128", "data": "synthetic", "config": {"workload": WORKLOAD, "modes": M, "photons": N_PH}}
+    times = []
+    if refshim.reference_available():
+        # the unmodified reference (pure Python, single-threaded) through its own public method:
+        # PermanentBackend.probability per output state, exactly the loop body of permanent.py:145-150
+        refshim.install()
+        from lightworks.emulator.backends.permanent import PermanentBackend as RefPermanent  # noqa: PLC0415
+        from lightworks.emulator.utils.state import fock_basis  # noqa: F401, PLC0415
+
+        sample = args.ref_sample or 20000
+        outs = O.fock_basis(M, N_PH, limit=sample).tolist()  # same order as fock_basis(24,10)[:sample]
+        backend = RefPermanent()
+        for step in range(args.warmup + args.steps):
+            n_do = min(sample, 2000) if step < args.warmup else sample
+            t0 = time.perf_counter()
+            for o in outs[:n_do]:
+                backend.probability(U, ins, o)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+        kind, cores = "reference", 1
+        desc = (f"unmodified lightworks {refshim.REFERENCE_ROOT} PermanentBackend.probability over the first {sample} "
+                "of 92561040 outputs per step (thewalrus.perm restated in C, see oracle/refshim); single thread: "
+                "the reference has no parallelism")
+    else:
+        threads = os.cpu_count() or 1
+        sample = args.ref_sample or 200000
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            O.basis_probabilities(U, ins, 0, sample if step >= args.warmup else 2000, threads=threads)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+        kind, cores = "port", threads
+        desc = f"oracle/lw_oracle.c port over the first {sample} outputs per step, {threads} pthreads"
+    total = sum(times)
+    value = sample * len(times) / total
+    line.update({"value": value, "ms_per_step": 1e3 * total / len(times),
+                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                 "gpu_launches": 0})
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def main() -> int:  # noqa: PLR0915
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ref-sample", type=int, default=0)
+    ap.add_argument("--cpu-sample", type=int, default=400000)
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import lightworks_b200 as lb
+    from lightworks_b200 import _lib, sharding
+    from oracle import oracle as O  # noqa: N812  (input generator + cpu_baseline leg only)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    warmup = max(args.warmup, 3)
+
+    ctx = lb.Context(local)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    U = O.random_unitary(M, SEED)  # noqa: N806  == lw.random_unitary(24, seed=3) (sdk/utils/random.py:66-67)
+    ins = np.array([1] * N_PH + [0] * (M - N_PH), dtype=np.uint8)
+    S = lb.fock_count(M, N_PH)  # noqa: N806
+    r0, r1 = sharding.rank_range(S, rank, world)
+    cnt = r1 - r0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        d_U = torch.from_numpy(U).cuda()  # noqa: N806  resident inputs for the device-timed region
+        d_ins = torch.from_numpy(ins).cuda()
+        d_probs = torch.empty(cnt, dtype=torch.float64, device="cuda")
+        d_full = torch.empty(S, dtype=torch.float64, device="cuda") if world > 1 else None
+        d_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    gather_sizes = [sharding.rank_range(S, r, world)[1] - sharding.rank_range(S, r, world)[0] for r in range(world)]
+
+    def device_step():
+        ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
+        if world > 1:
+            outs = list(torch.split(d_full, gather_sizes))
+            if len(set(gather_sizes)) == 1:
+                dist.all_gather_into_tensor(d_full, d_probs)
+            else:
+                dist.all_gather(outs, d_probs)
+            torch.sum(d_probs, dim=0, keepdim=True, out=d_sum)
+            dist.all_reduce(d_sum)
+
+    # pinned host buffers for the end-to-end leg
+    h_U = torch.from_numpy(U.copy()).pin_memory()  # noqa: N806
+    h_ins = torch.from_numpy(ins.copy()).pin_memory()
+    h_out = torch.empty(cnt, dtype=torch.float64).pin_memory()
+    h_U_np, h_ins_np, h_out_np = h_U.numpy(), h_ins.numpy(), h_out.numpy()  # noqa: N806
+
+    def e2e_step():
+        # the public host-buffer API: H2D of U + input, kernel, D2H of this rank's probabilities, sync
+        ctx.perm_basis_probs(h_U_np, h_ins_np, r0, cnt, out=h_out_np)
+        if world > 1:
+            t = torch.tensor([float(h_out_np.sum())], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t)
+
+    def timed(step_fn, k, sampler=None):
+        """K steps between barrier+synchronize; per-step CUDA events on the launch stream; the L2 flush
+        between steps is not inside any event pair.  Returns (sum of event ms, wall ms)."""
+        evs = []
+        barrier()
+        if sampler:
+            sampler.start()
+        w0 = time.perf_counter()
+        with torch.cuda.stream(stream):
+            for _ in range(k):
+                flush.fill_(1)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                step_fn()
+                e1.record(stream)
+                evs.append((e0, e1))
+        barrier()
+        wall = (time.perf_counter() - w0) * 1e3
+        clocks = sampler.stop() if sampler else None
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms, wall, clocks
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    # ---- warm-up, then the device-resident timed region ----
+    with torch.cuda.stream(stream):
+        for _ in range(warmup):
+            device_step()
+    l0 = ctx.launch_count()
+    dev_ms, dev_wall, clocks = timed(device_step, args.steps, ClockSampler(local))
+    launches = ctx.launch_count() - l0
+    dev_ms = max_over_ranks(dev_ms)
+    total_sum = float(d_probs.sum()) if world == 1 else float(d_sum)
+    value = S * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end through the host-buffer C ABI ----
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = S * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (K1 perm_states_kernel<10,...>) ----
+    peak = ctx.fp64_peak()  # measured live: MEASURED_PEAKS.json carries no FP64 entry
+    with torch.cuda.stream(stream):
+        kev = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
+            e1.record(stream)
+            kev.append((e0, e1))
+        stream.synchronize()
+    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
+    achieved = cnt * flops_per_perm(N_PH) / (k_ms * 1e-3)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp64", "kernel": "perm_states_kernel<N=10> (batched Glynn/Gray-code permanents)",
+                "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel_ms": k_ms,
+                "flops_per_unit": flops_per_perm(N_PH), "units_per_launch": cnt,
+                "peak_source": "lwb_fp64_peak DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no "
+                               "FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)",
+                "note": "tensor cores unused: not a dense contraction; ceiling of the 6n-2 instruction Glynn step "
+                        "is (8n-4)/(12n-4) = 0.655 of DFMA peak at n=10"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "c128", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "modes": M, "photons": N_PH, "outputs": S,
+                   "parallelism": f"fock-rank-range shards x{world}" + (" + NCCL all-gather/all-reduce" if world > 1 else ""),
+                   "l2": "256 MiB flush between timed steps (outside the event pairs); outputs 740 MB > 126 MB L2",
+                   "check_sum_of_probabilities": total_sum},
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(U.nbytes + ins.nbytes),
+                "d2h_bytes_per_step": int(cnt * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
+                "api": "lwb_perm_basis_probs (host buffers, pinned) via lightworks_b200.Context.perm_basis_probs"},
+        "gpu_launches": int(launches), "clocks": clocks, "wall_ms_timed_region": dev_wall,
+    }
+
+    if rank == 0 and world == 1:
+        threads = os.cpu_count() or 1
+        line["cpu_baseline"] = cpu_port_baseline(U, ins, args.cpu_sample, threads)
+        if not args.no_extras:
+            line["extra"] = extras(ctx, stream, peak, d_U, torch, np, O, _lib)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
+    """Other rows of the metric (reported, not the headline): SLOS probabilities/s on the same
+    distribution, batched n x n permanents/s for n = 12, 16, 20 and single large permanents."""
+    out = {}
+
+    def t_ms(fn, reps=3):
+        with torch.cuda.stream(stream):
+            fn()
+            stream.synchronize()
+            ts = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+                e1.synchronize()
+                ts.append(e0.elapsed_time(e1))
+        return min(ts)
+
+    S = _lib.fock_count(M, N_PH)  # noqa: N806
+    ins = [1] * N_PH + [0] * (M - N_PH)
+    with torch.cuda.stream(stream):
+        d_p = torch.empty(S, dtype=torch.float64, device="cuda")
+    ms = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1))
+    from math import comb
+
+    slos_bytes = sum(16 * (comb(M + k - 2, k - 1) + comb(M + k - 1, k)) for k in range(1, N_PH + 1))
+    out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms, "algorithmic_GBps": slos_bytes / (ms * 1e-3) / 1e9,
+                      "note": "SLOS backend, same distribution, SLOS dict order, all layers + reorder"}
+    del d_p
+    for n in (12, 16, 20):
+        B = int(max(2e11 / flops_per_perm(n), 148 * 64))  # noqa: N806
+        with torch.cuda.stream(stream):
+            A = torch.randn(B, n, n, 2, dtype=torch.float64, device="cuda") / np.sqrt(n)  # noqa: N806
+            o = torch.empty(B, 2, dtype=torch.float64, device="cuda")
+        ms = t_ms(lambda: ctx.perm_matrices_dev(A, B, n, o))
+        out[f"batched_perm_n{n}"] = {"permanents_per_s": B / (ms * 1e-3), "batch": B, "ms": ms,
+                                     "fp64_frac": B * flops_per_perm(n) / (ms * 1e-3) / peak}
+        del A, o
+    U60 = O.random_unitary(60, 5)  # noqa: N806
+    for n in (24, 28):
+        with torch.cuda.stream(stream):
+            A = torch.from_numpy(U60[:n, :n].copy()).cuda()  # noqa: N806
+            o2 = torch.empty(2, dtype=torch.float64, device="cuda")
+        ms = t_ms(lambda: ctx.perm_single_dev(A, n, o2))
+        out[f"single_perm_n{n}"] = {"permanents_per_s": 1e3 / ms, "ms": ms, "fp64_frac": flops_per_perm(n) / (ms * 1e-3) / peak}
+    return out
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -88,7 +88,7 @@ def test_sampler_distribution_and_samples(lw, name):
         circ.loss(i, 0.1)
     src = Source(purity=0.95, brightness=0.9, indistinguishability=0.9)
     mk = lambda: lw.Sampler(circ, lw.State([1, 0, 1, 0, 1, 0]), 2000, source=src,  # noqa: E731
-                            detector=Detector(efficiency=0.9), random_seed=7)
+                            detector=Detector(efficiency=0.9), sampling_mode="input", random_seed=7)
     t1, t2 = mk(), mk()
     r1 = Backend(name).run(t1)
     r2 = Backend(name + "_cpu").run(t2)
