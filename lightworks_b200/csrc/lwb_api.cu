@@ -560,7 +560,7 @@ static int slos_layers(lwb_handle h, const double* d_U, int m, const uint8_t* in
         a.bin = h->d_bin; a.m = m; a.k = k; a.S = binom(hb, m + k - 1, k);
         a.parent = bufs[cur]; a.child = bufs[cur ^ 1]; a.U = (const double2*)d_U; a.in_mode = modes[k - 1];
         a.sqrt_tab = (const double*)h->bSmall.p + 2;
-        const size_t smem = (size_t)(m + k) * (k + 1) * 8 + (size_t)m * 16 + (size_t)(k + 1) * 8;
+        const size_t smem = ((((size_t)(m + k) * (k + 1)) + 1) & ~(size_t)1) * 8 + (size_t)m * 16 + (size_t)(k + 1) * 8;
         CK(launch_kmax(h, k, a.S, smem, a, slos_layer_kernel<4>, slos_layer_kernel<8>, slos_layer_kernel<12>,
                        slos_layer_kernel<16>, slos_layer_kernel<24>, slos_layer_kernel<40>));
         cur ^= 1;

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(SLOS_THREADS) slos_layer_kernel(SlosLayerArgs 
     const int k = a.k, m = a.m;
     const int bw = k + 1, bh = m + k;
     uint64_t* sb = reinterpret_cast<uint64_t*>(smem_raw);
-    double2* ucol = reinterpret_cast<double2*>(sb + (size_t)bh * bw);
+    double2* ucol = reinterpret_cast<double2*>(sb + (((size_t)bh * bw + 1) & ~(size_t)1));  // keep 16-byte alignment
     double* sq = reinterpret_cast<double*>(ucol + m);
     for (int e = threadIdx.x; e < bh * bw; e += SLOS_THREADS) sb[e] = a.bin[(e / bw) * LWB_BIN_B + (e % bw)];
     for (int e = threadIdx.x; e < m; e += SLOS_THREADS) ucol[e] = a.U[(size_t)e * m + a.in_mode];
