@@ -125,6 +125,9 @@ int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const 
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */
 int lwb_fp64_peak(lwb_handle h, double* flops_per_s);
+/* FP64 issue-rate probes for register-operand patterns (1: 3-register DFMA, 2: DFMA with a shared
+ * operand, 3: DMUL, 4: DADD, 5: complex-multiply chain); reported as instructions x 2 flops / s. */
+int lwb_fp64_probe(lwb_handle h, int mode, double* flops_per_s);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ SIGNATURES = {
     "lwb_slos_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "lwb_pdist": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _i, _vp, _vp, _u64, _pu64]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
+    "lwb_fp64_probe": (_i, [_vp, _i, _pdbl]),
 }
 
 _cdll = None
@@ -201,6 +202,11 @@ class Context:
     def fp64_peak(self) -> float:
         out = C.c_double(0)
         check(cdll().lwb_fp64_peak(self._h, C.byref(out)))
+        return float(out.value)
+
+    def fp64_probe(self, mode: int) -> float:
+        out = C.c_double(0)
+        check(cdll().lwb_fp64_probe(self._h, mode, C.byref(out)))
         return float(out.value)
 
     # -- host-buffer entry points --

@@ -479,6 +479,48 @@ int lwb_perm_single(lwb_handle h, const double* A, int n, int dtype, int slice, 
     return 0;
 }
 
+int lwb_fp64_probe(lwb_handle h, int mode, double* flops_per_s) {
+    if (!h || !flops_per_s) return fail(LWB_E_ARG, "null argument");
+    if (mode < 1 || mode > 5) return fail(LWB_E_ARG, "mode %d", mode);
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bTmp, 8 * 1024));
+    double host[24];
+    for (int i = 0; i < 24; ++i) host[i] = (i < 8) ? 1.0 + 1e-7 * i : (i < 16 ? 1e-9 * (i - 7) : 0.5 + 0.01 * i);
+    if (mode == 3) for (int i = 0; i < 8; ++i) host[i] = 1.0 + 1e-12 * i;
+    if (mode == 5) for (int i = 0; i < 8; ++i) { host[i] = 0.9999999; host[8 + i] = 1e-4; }
+    CU(cudaMemcpyAsync((char*)h->bTmp.p + 4096, host, sizeof host, cudaMemcpyHostToDevice, h->stream));
+    const int iters = 2048, blocks = h->sm_count * 4, threads = 256;
+    const double per_iter = (mode == 5) ? 32.0 : 8.0;  // FP64 instructions per thread per iteration
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(e0, h->stream));
+        double* o = (double*)h->bTmp.p;
+        const double* src = (const double*)((char*)h->bTmp.p + 4096);
+        switch (mode) {
+            case 1: fp64_probe_kernel<1><<<blocks, threads, 0, h->stream>>>(o, iters, src); break;
+            case 2: fp64_probe_kernel<2><<<blocks, threads, 0, h->stream>>>(o, iters, src); break;
+            case 3: fp64_probe_kernel<3><<<blocks, threads, 0, h->stream>>>(o, iters, src); break;
+            case 4: fp64_probe_kernel<4><<<blocks, threads, 0, h->stream>>>(o, iters, src); break;
+            default: fp64_probe_kernel<5><<<blocks, threads, 0, h->stream>>>(o, iters, src); break;
+        }
+        h->launches++;
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * per_iter * (double)iters * blocks * threads / (ms * 1e-3);
+        if (rep > 0) best = std::max(best, flops);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *flops_per_s = best;
+    return 0;
+}
+
 int lwb_fp64_peak(lwb_handle h, double* flops_per_s) {
     if (!h || !flops_per_s) return fail(LWB_E_ARG, "null argument");
     std::lock_guard<std::mutex> lk(h->mu);

@@ -39,4 +39,59 @@ static __global__ void dfma_peak_kernel(double* out, int iters, double a) {
     if (s == 123.456) out[0] = s;  // keep the chains alive
 }
 
+// FP64 pipe issue-rate probes (register-operand patterns).  Each thread runs 8 independent dependency
+// chains; `mode` picks the instruction pattern.  Rates are reported as if every instruction were a
+// DFMA (2 flops), so 1.0 x lwb_fp64_peak = one FP64 warp-instruction per 2 cycles per scheduler.
+//   1: DFMA x = a_i * b_i + x      (3 distinct register operands)
+//   2: DFMA x = a   * b_i + x      (operand A shared by consecutive instructions: reuse cache)
+//   3: DMUL x = x * a_i            (2 register operands)
+//   4: DADD x = x + a_i            (2 register operands)
+//   5: complex multiply chain p *= v_i written as in glynn.cuh (2 DMUL + 2 DFMA)
+template <int MODE>
+static __global__ void fp64_probe_kernel(double* out, int iters, const double* __restrict__ src) {
+    double a[8], b[8], x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // lane-dependent so nothing is promoted to uniform registers
+        a[i] = src[i] + threadIdx.x * 1e-9; b[i] = src[8 + i] + threadIdx.x * 1e-12; x[i] = src[16 + i] + threadIdx.x * 1e-7;
+    }
+    const double a0 = a[0];
+#pragma unroll 4
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fma(a[i], b[i], x[i]);
+        } else if (MODE == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = fma(a0, b[i], x[i]);
+        } else if (MODE == 3) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = x[i] * a[i];
+        } else if (MODE == 4) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[i] = x[i] + a[i];
+        } else {
+            // 4 independent complex products (x[2c], x[2c+1]) *= (a[2c], b[2c]) then *= (a[2c+1], b[2c+1])
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double pr = x[2 * c], pi = x[2 * c + 1];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const double ar = a[2 * c + k], ai = b[2 * c + k];
+                    double nr = pr * ar, ni = pr * ai;
+                    nr = fma(-pi, ai, nr);
+                    ni = fma(pi, ar, ni);
+                    pr = nr;
+                    pi = ni;
+                }
+                x[2 * c] = pr;
+                x[2 * c + 1] = pi;
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    if (s == 123.456) out[0] = s;
+}
+
 }  // namespace lwb

@@ -15,7 +15,9 @@ namespace lwb {
 
 constexpr int K1_THREADS = 256;
 #ifndef LWB_U
-#define LWB_U 3   /* K1: statically unrolled low Gray bits (measured best of 1,2,3 on B200) */
+/* K1: statically unrolled low Gray bits.  Measured on B200 (profiles/r01_variant_sweep.md): 4 is best up to
+ * n = 14, 3 beyond (register pressure); capping registers with __launch_bounds__ minBlocks only spills. */
+#define LWB_U(N) ((N) <= 14 ? 4 : 3)
 #endif
 #ifndef LWB_U2
 #define LWB_U2 2  /* K2 */
@@ -29,7 +31,7 @@ template <int N, int LOG_L>
 struct K1Shape {
     static constexpr int L = 1 << LOG_L;
     static constexpr int C = N - 1 - LOG_L;          // steps per lane = 2^C
-    static constexpr int U = C < LWB_U ? C : LWB_U;  // statically unrolled low bits
+    static constexpr int U = C < LWB_U(N) ? C : LWB_U(N);  // statically unrolled low bits
     static constexpr int GPB = K1_THREADS / L;       // groups (permanents in flight) per block
 };
 
