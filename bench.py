@@ -246,10 +246,8 @@ def main() -> int:  # noqa: PLR0915
 
     def e2e_step():
         # the public host-buffer API: H2D of U + input, kernel, D2H of this rank's probabilities, sync
+        # (every rank ends with its rank-range shard in its own host buffer; no host-side reduction)
         ctx.perm_basis_probs(h_U_np, h_ins_np, r0, cnt, out=h_out_np)
-        if world > 1:
-            t = torch.tensor([float(h_out_np.sum())], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t)
 
     def timed(step_fn, k, sampler=None):
         """K steps between barrier+synchronize; per-step CUDA events on the launch stream; the L2 flush

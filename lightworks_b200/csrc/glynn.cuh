@@ -182,4 +182,87 @@ __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __rest
     acc_im = fma(s0, si, acc_im);
 }
 
+// A contiguous RANGE of chunks [q_begin, q_begin + n_chunks) walked by one lane without re-deriving the
+// start vector: inside a chunk the flips are the uniform ruler sequence (broadcast row reads, as in
+// glynn_chunk); between chunk q and q+1 the Gray code flips row C + ctz(q+1), which differs per lane and is
+// read with a lane-specific address once every 2^C steps.  Term signs: parity(popcount(gray(g))) = g & 1,
+// so the sign alternates with the step index and needs no per-chunk correction (C >= 1).
+// Used by the single-large-permanent kernel: every lane of the GPU owns an equal share of the Gray space
+// regardless of how 2^(n-1) divides by the lane count (no tail quantisation, one setup per lane).
+template <int N, int C, int U, typename T>
+__device__ __forceinline__ void glynn_range(const typename vec2<T>::type* __restrict__ rows,
+                                            const int* __restrict__ rowidx, uint64_t q_begin, uint64_t n_chunks,
+                                            T& acc_re, T& acc_im) {
+    static_assert(U <= C && C <= N - 1 && C >= 1, "bad chunk shape");
+    using V = typename vec2<T>::type;
+    if (n_chunks == 0) return;
+    T wr[N], wi[N];
+    const uint64_t g0 = q_begin << C;
+    const uint64_t gr0 = g0 ^ (g0 >> 1);
+    {
+        const V* r = rows + lds_i(rowidx + N - 1);
+#pragma unroll
+        for (int j = 0; j < N; ++j) { V a = lds_c(r, j); wr[j] = a.x; wi[j] = a.y; }
+    }
+#pragma unroll
+    for (int i = 0; i < N - 1; ++i) {
+        const V* r = rows + lds_i(rowidx + i);
+        if (i < C - 1) row_addsub<N, T, false>(wr, wi, r);
+        else row_fma<N, T>(wr, wi, r, ((gr0 >> i) & 1) ? T(-1) : T(1));
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { wr[j] *= T(0.5); wi[j] *= T(0.5); }
+    const V* lowrow[U > 0 ? U : 1];
+#pragma unroll
+    for (int k = 0; k < U; ++k) lowrow[k] = rows + lds_i(rowidx + k);
+
+    T sr = T(0), si = T(0);
+    constexpr uint32_t NBLK = 1u << (C - U);
+    constexpr int BLK = 1 << U;
+#pragma unroll 1
+    for (uint64_t c = 0; c < n_chunks; ++c) {
+        const uint64_t q = q_begin + c;
+#pragma unroll 1
+        for (uint32_t ob = 0; ob < NBLK; ++ob) {
+#pragma unroll
+            for (int t = 0; t < BLK; ++t) {
+                T pr, pi;
+                cprod<N, T>(wr, wi, pr, pi);
+                if ((t & 1) && BLK > 1) { sr -= pr; si -= pi; }
+                else if (BLK > 1 || !(ob & 1)) { sr += pr; si += pi; }
+                else { sr -= pr; si -= pi; }
+                if (t + 1 < BLK) {
+                    const int t1 = t + 1;
+                    const int k = cx_ctz(t1);
+                    if (k <= U - 2) {
+                        const bool newbit = ((t1 >> k) ^ (t1 >> (k + 1))) & 1;
+                        if (newbit) row_addsub<N, T, true>(wr, wi, lowrow[k]);
+                        else row_addsub<N, T, false>(wr, wi, lowrow[k]);
+                    } else {
+                        const uint32_t hi = (U == C) ? (uint32_t)(q & 1u) : (ob & 1u);
+                        row_fma<N, T>(wr, wi, lowrow[k], hi ? T(1) : T(-1));
+                    }
+                }
+            }
+            if (ob + 1 < NBLK) {
+                const uint32_t o1 = ob + 1;
+                const int k = U + (__ffs(o1) - 1);
+                uint32_t newbit;
+                if (k == C - 1) newbit = 1u ^ (uint32_t)(q & 1u);
+                else newbit = ((o1 >> (k - U)) ^ (o1 >> (k - U + 1))) & 1u;
+                row_fma<N, T>(wr, wi, rows + lds_i(rowidx + k), newbit ? T(-1) : T(1));
+            }
+        }
+        if (c + 1 < n_chunks) {  // chunk boundary: lane-specific row
+            const uint64_t q1 = q + 1;
+            const int z = __ffsll((long long)q1) - 1;
+            const int k = C + z;
+            const uint32_t newbit = (uint32_t)((q1 >> z) ^ (q1 >> (z + 1))) & 1u;
+            row_fma<N, T>(wr, wi, rows + lds_i(rowidx + k), newbit ? T(-1) : T(1));
+        }
+    }
+    acc_re += sr;
+    acc_im += si;
+}
+
 }  // namespace lwb

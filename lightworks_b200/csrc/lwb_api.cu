@@ -51,6 +51,8 @@ struct lwb_context {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernel
+    cudaEvent_t chunk_done[8] = {};
     uint64_t* d_bin = nullptr;
     Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall;
     uint64_t launches = 0;
@@ -142,6 +144,8 @@ int lwb_create(int device, lwb_handle* out) {
     CU(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
     CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
+    CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (auto& e : h->chunk_done) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CU(cudaMalloc(&h->d_bin, sizeof g_bin));
     CU(cudaMemcpy(h->d_bin, host_bin(), sizeof g_bin, cudaMemcpyHostToDevice));
     load_tables();
@@ -158,6 +162,8 @@ int lwb_destroy(lwb_handle h) {
         if (b->p) cudaFree(b->p);
     if (h->d_bin) cudaFree(h->d_bin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto& e : h->chunk_done) if (e) cudaEventDestroy(e);
     delete h;
     return 0;
 }
@@ -427,10 +433,23 @@ int lwb_perm_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in
     CK(ensure(h, h->bRes, cnt * 8));
     CU(cudaMemcpyAsync(h->bU.p, U, (size_t)m * m * 16, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->bIn.p, in_state, (size_t)m, cudaMemcpyHostToDevice, h->stream));
-    CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, 1, nullptr, r0, cnt, n, dtype, 1,
-                     (double*)h->bRes.p));
-    CU(cudaMemcpyAsync(probs, h->bRes.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+    // Large ranges are cut into chunks so the device-to-host copy of chunk c overlaps the kernel of chunk c+1
+    // (the copy is the only host<->device traffic of this path: 8 bytes per state).
+    const int chunks = cnt >= (4u << 20) ? 8 : 1;
+    for (int c = 0; c < chunks; ++c) {
+        const uint64_t b = cnt * (uint64_t)c / chunks, e = cnt * (uint64_t)(c + 1) / chunks;
+        CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, 1, nullptr, r0 + b, e - b, n, dtype, 1,
+                         (double*)h->bRes.p + b));
+        if (chunks == 1) {
+            CU(cudaMemcpyAsync(probs, h->bRes.p, cnt * 8, cudaMemcpyDeviceToHost, h->stream));
+        } else {
+            CU(cudaEventRecord(h->chunk_done[c], h->stream));
+            CU(cudaStreamWaitEvent(h->copy_stream, h->chunk_done[c], 0));
+            CU(cudaMemcpyAsync(probs + b, (double*)h->bRes.p + b, (e - b) * 8, cudaMemcpyDeviceToHost, h->copy_stream));
+        }
+    }
     CU(cudaStreamSynchronize(h->stream));
+    if (chunks > 1) CU(cudaStreamSynchronize(h->copy_stream));
     return 0;
 }
 
@@ -443,12 +462,13 @@ int lwb_perm_single_dev(lwb_handle h, const double* d_A, int n, int dtype, int s
     load_tables();
     if (!g_k2[n]) return fail(LWB_E_LIMIT, "no single-permanent kernel for n=%d", n);
     const int C = g_k2[n]->chunk_bits;
-    const uint64_t Q = 1ull << (n - 1 - C);
+    const uint64_t Q = (n - 1 - C) > 0 ? 1ull << (n - 1 - C) : 1ull;  // chunks of 2^C Gray steps
     const uint64_t qb = Q * (uint64_t)slice / (uint64_t)n_slices, qe = Q * (uint64_t)(slice + 1) / (uint64_t)n_slices;
     auto fn = g_k2[n]->single[dtype];
     int resident = 0;
     CK(resident_blocks(h, fn, 0, &resident));
-    uint64_t need = (qe - qb + K1_THREADS - 1) / K1_THREADS;
+    // every lane walks a contiguous range of chunks; aim for >= 4 chunks per lane before adding blocks
+    uint64_t need = (qe - qb + 4 * K1_THREADS - 1) / (4 * K1_THREADS);
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)resident));
     CK(ensure(h, h->bPart, (size_t)grid * 16));
     if (qe > qb) {
@@ -573,15 +593,39 @@ static int launch_kmax(lwb_handle h, int n, uint64_t threads_needed, size_t smem
     return 0;
 }
 
-// Runs every SLOS layer; on return *final points at the device layer holding the S(m,n) amplitudes in
-// colex order (one of the handle's two layer buffers).
-static int slos_layers(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int n, const double2** final) {
+template <typename IDX>
+static int launch_slos_layer(lwb_handle h, const SlosLayerArgs& a) {
+    const int k = a.k, m = a.m;
+    const size_t smem = (size_t)m * 16 + (size_t)((k + 2) & ~1) * 8 + 3 * (size_t)k * (m + 1) * sizeof(IDX);
+    const uint64_t warps = (a.S + 32ull * SLOS_ITERS - 1) / (32ull * SLOS_ITERS);
+    const unsigned grid = (unsigned)((warps + SLOS_THREADS / 32 - 1) / (SLOS_THREADS / 32));
+#define LWB_GO(KM)                                                                                         \
+    do {                                                                                                   \
+        auto fn = slos_layer_kernel<KM, IDX>;                                                              \
+        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        fn<<<grid, SLOS_THREADS, smem, h->stream>>>(a);                                                    \
+    } while (0)
+    if (k <= 4) LWB_GO(4);
+    else if (k <= 8) LWB_GO(8);
+    else if (k <= 12) LWB_GO(12);
+    else if (k <= 16) LWB_GO(16);
+    else if (k <= 24) LWB_GO(24);
+    else LWB_GO(40);
+#undef LWB_GO
+    h->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// Runs every SLOS layer (all layers in SLOS / lexicographic order).  The last layer is written to `final_dst`
+// (S(m,n) complex amplitudes, or S(m,n) doubles |a|^2 when final_probs).
+static int slos_layers(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int n, void* final_dst,
+                       int final_probs) {
     const uint64_t* hb = host_bin();
-    const uint64_t S = binom(hb, m + n - 1, n);
-    const uint64_t Sp = n >= 1 ? binom(hb, m + n - 2, n - 1) : 1;
-    // ping-pong so that the last layer lands in bLayerA
-    CK(ensure(h, h->bLayerA, std::max<uint64_t>(S, 1) * 16));
-    CK(ensure(h, h->bLayerB, std::max<uint64_t>(Sp, 1) * 16));
+    const uint64_t Sp1 = n >= 1 ? binom(hb, m + n - 2, n - 1) : 1;  // layer n-1
+    const uint64_t Sp2 = n >= 2 ? binom(hb, m + n - 3, n - 2) : 1;  // layer n-2
+    CK(ensure(h, h->bLayerA, std::max<uint64_t>(Sp1, 1) * 16));
+    CK(ensure(h, h->bLayerB, std::max<uint64_t>(Sp2, 1) * 16));
     CK(ensure(h, h->bSmall, 4096));
     double vf = 1.0;  // vector_factorial, slos.py:126-128
     int modes[LWB_MAX_PHOTONS + 1];
@@ -593,21 +637,21 @@ static int slos_layers(lwb_handle h, const double* d_U, int m, const uint8_t* in
     host_small[1] = 0.0;
     for (int k = 0; k <= n; ++k) host_small[2 + k] = pow((double)k, 0.5);  // key[mode] ** 0.5, slos.py:121
     CU(cudaMemcpyAsync(h->bSmall.p, host_small, sizeof(double) * (size_t)(n + 3), cudaMemcpyHostToDevice, h->stream));
-    // layer 0 goes into the buffer that makes layer n end in A
+    // ping-pong so that layer n-1 lands in A (the larger buffer): layer j lives in A iff (n-1-j) is even
     double2* bufs[2] = {(double2*)h->bLayerA.p, (double2*)h->bLayerB.p};
-    int cur = (n % 2 == 0) ? 0 : 1;
-    CU(cudaMemcpyAsync(bufs[cur], h->bSmall.p, 16, cudaMemcpyDeviceToDevice, h->stream));
+    auto buf_of = [&](int j) { return bufs[((n - 1 - j) % 2 + 2) % 2]; };
+    CU(cudaMemcpyAsync(n == 0 ? final_dst : (void*)buf_of(0), h->bSmall.p, 16, cudaMemcpyDeviceToDevice, h->stream));
     for (int k = 1; k <= n; ++k) {
         SlosLayerArgs a;
         a.bin = h->d_bin; a.m = m; a.k = k; a.S = binom(hb, m + k - 1, k);
-        a.parent = bufs[cur]; a.child = bufs[cur ^ 1]; a.U = (const double2*)d_U; a.in_mode = modes[k - 1];
+        a.parent = buf_of(k - 1);
+        a.child = (k == n) ? final_dst : (void*)buf_of(k);
+        a.U = (const double2*)d_U; a.in_mode = modes[k - 1];
         a.sqrt_tab = (const double*)h->bSmall.p + 2;
-        const size_t smem = ((((size_t)(m + k) * (k + 1)) + 1) & ~(size_t)1) * 8 + (size_t)m * 16 + (size_t)(k + 1) * 8;
-        CK(launch_kmax(h, k, a.S, smem, a, slos_layer_kernel<4>, slos_layer_kernel<8>, slos_layer_kernel<12>,
-                       slos_layer_kernel<16>, slos_layer_kernel<24>, slos_layer_kernel<40>));
-        cur ^= 1;
+        a.write_probs = (k == n) ? final_probs : 0;
+        if (a.S < (1ull << 32)) CK(launch_slos_layer<uint32_t>(h, a));
+        else CK(launch_slos_layer<uint64_t>(h, a));
     }
-    *final = bufs[cur];
     return 0;
 }
 
@@ -620,7 +664,7 @@ static int slos_check(int m, const uint8_t* in_state, int* n_out) {
     return 0;
 }
 
-// out_mode: 0 complex amplitudes, 1 probabilities
+// out_mode: 0 complex amplitudes, 1 probabilities; order: 1 = SLOS (native), 0 = fock_basis (reordered)
 static int slos_run_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order, int out_mode,
                         double* d_out) {
     int n = 0;
@@ -628,20 +672,20 @@ static int slos_run_dev(lwb_handle h, const double* d_U, int m, const uint8_t* i
     if (order != 0 && order != 1) return fail(LWB_E_ARG, "order %d", order);
     CU(cudaSetDevice(h->device));
     const uint64_t S = binom(host_bin(), m + n - 1, n);
-    const double2* fin = nullptr;
-    CK(slos_layers(h, d_U, m, in_state, n, &fin));
-    if (order == 0) {
-        if (out_mode == 0) CU(cudaMemcpyAsync(d_out, fin, S * 16, cudaMemcpyDeviceToDevice, h->stream));
-        else {
-            abs2_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(fin, S, d_out);
-            h->launches++;
-            CU(cudaGetLastError());
+    if (order == 1 || n == 0) {
+        if (n == 0 && out_mode == 1) {
+            const double one = 1.0;
+            CU(cudaMemcpyAsync(d_out, &one, 8, cudaMemcpyHostToDevice, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            return 0;
         }
-    } else {
-        ReorderArgs ra{h->d_bin, m, n, S, (const double*)fin, d_out, out_mode};
-        CK(launch_kmax(h, n, S, 0, ra, reorder_lex_kernel<4>, reorder_lex_kernel<8>, reorder_lex_kernel<12>,
-                       reorder_lex_kernel<16>, reorder_lex_kernel<24>, reorder_lex_kernel<40>));
+        return slos_layers(h, d_U, m, in_state, n, d_out, out_mode);
     }
+    CK(ensure(h, h->bTmp, S * 16));
+    CK(slos_layers(h, d_U, m, in_state, n, h->bTmp.p, 0));
+    ReorderArgs ra{h->d_bin, m, n, S, (const double*)h->bTmp.p, d_out, out_mode};
+    CK(launch_kmax(h, n, S, 0, ra, reorder_to_colex_kernel<4>, reorder_to_colex_kernel<8>, reorder_to_colex_kernel<12>,
+                   reorder_to_colex_kernel<16>, reorder_to_colex_kernel<24>, reorder_to_colex_kernel<40>));
     return 0;
 }
 

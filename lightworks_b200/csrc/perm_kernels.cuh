@@ -235,8 +235,11 @@ struct PermSingleArgs {
 
 template <int N>
 struct K2Shape {
-    static constexpr int C0 = N - 16;
-    static constexpr int C = C0 < 4 ? (N - 1 < 4 ? N - 1 : 4) : (C0 > 10 ? 10 : C0);
+    // chunk bits: every lane gets a contiguous range of ~28+ chunks (glynn_range), so C only has to keep the
+    // lane-specific boundary flips rare; small n cannot fill the GPU anyway (use the batched kernel there)
+    static constexpr int C0 = N - 21;
+    static constexpr int CC = C0 < 3 ? 3 : (C0 > 7 ? 7 : C0);
+    static constexpr int C = CC > N - 1 ? (N - 1 < 1 ? 1 : N - 1) : CC;
     static constexpr int U = C < LWB_U2 ? C : LWB_U2;
 };
 
@@ -257,19 +260,22 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermS
         Ms[e] = v;
     }
     __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * K1_THREADS;
-    // every lane of a warp runs the same number of chunks (uniform control flow for broadcast reads);
-    // lanes past q_end redo the last chunk with weight 0
     double dr = 0.0, di = 0.0;
-    const uint64_t warp_first = a.q_begin + (uint64_t)blockIdx.x * K1_THREADS + (tid & ~31);
-    for (uint64_t qw = warp_first; qw < a.q_end; qw += stride) {
-        uint64_t q = qw + (tid & 31);
-        const bool live = q < a.q_end;
-        if (!live) q = a.q_end - 1;
+    if constexpr (N == 1) {
+        if (blockIdx.x == 0 && tid == 0 && a.q_begin < a.q_end) { dr = 0.5 * (double)Ms[0].x; di = 0.5 * (double)Ms[0].y; }
+    } else {
+        // equal contiguous shares of the chunk range for every lane of the grid
+        const uint64_t lanes = (uint64_t)gridDim.x * K1_THREADS;
+        const uint64_t lane = (uint64_t)blockIdx.x * K1_THREADS + tid;
+        const uint64_t total = a.q_end - a.q_begin;
+        const uint64_t b = a.q_begin + (total / lanes) * lane + (lane < total % lanes ? lane : total % lanes);
+        const uint64_t cnt = total / lanes + (lane < total % lanes ? 1 : 0);
         T sr = T(0), si = T(0);
-        glynn_chunk<N, S::C, S::U, T>(Ms, ident, (uint32_t)q, sr, si);
-        if (live) { dr += (double)sr; di += (double)si; }
+        glynn_range<N, S::C, S::U, T>(Ms, ident, b, cnt, sr, si);
+        dr = (double)sr;
+        di = (double)si;
     }
+    __syncwarp();
     dr = group_sum<double>(dr, 5);
     di = group_sum<double>(di, 5);
     if ((tid & 31) == 0) { red[0][tid >> 5] = dr; red[1][tid >> 5] = di; }

@@ -3,22 +3,27 @@
 //  K3  slos_layer_kernel     : one photon-addition layer of SLOSBackend.calculate
 //                              (lightworks/emulator/backends/slos.py:96-103, a_i_dagger :108-123,
 //                              add_dicts :131-138) in gather form over rank-indexed layers.
-//  K4a reorder_kernel        : colex (fock_basis) order -> SLOS dict-insertion (lexicographic) order,
-//                              optionally |a|^2.
+//  K4a reorder_to_colex_kernel: SLOS (lexicographic) order -> fock_basis (colex) order.
 //  K4b marginalise_kernel    : threshold + loss-mode marginalisation with first-seen bookkeeping
 //                              (permanent.py:148-157, slos.py:73-79).
 //
-// Layer k holds one complex128 amplitude per Fock state of k photons in m modes, indexed by the
-// colex rank of fock.cuh.  The reference applies, for input photon number k (in mode i_k),
+// Every layer k holds one complex128 amplitude per Fock state of k photons in m modes, stored in the
+// reference's own SLOS order (dict insertion order = lexicographic order of the ascending mode list
+// x_0 <= ... <= x_{k-1}), so the final layer needs no permutation.  The reference applies, for the k-th
+// input photon (in mode i_k),
 //     out[t] = sum_j sqrt(t_j) * in[t - e_j] * U[j, i_k]          (j ascending, slos.py:98-103)
-// The kernel evaluates exactly that sum per child state t, in the same j order and with the same
-// rounding sequence (no FMA contraction): (sqrt(t_j) * value) * U[j,i] then complex add, so the
-// amplitudes agree with the reference's dict arithmetic bit for bit (e.g. the exact 0 of the HOM
-// dip, tests/emulator/backend_test.py:236).
+// The kernel evaluates exactly that sum per child state t, in the same j order and with the same rounding
+// sequence (no FMA contraction): (sqrt(t_j) * value) * U[j,i] then complex add, so amplitudes agree with the
+// reference's dict arithmetic bit for bit in practice (e.g. the exact 0 of the HOM dip,
+// tests/emulator/backend_test.py:236).
 //
-// Parent rank without re-ranking: with A_i = C(x_i+i-1, i) and B_i = C(x_i+i-2, i-1) (1-based i over
-// the ascending mode list x), removing the element at position p gives
-//     rank(t - e_{x_p}) = sum_{i<p} A_i + sum_{i>p} B_i .
+// Indexing.  With G(v, r) = C(m-v+r, r+1) (non-decreasing lists of length r+1 over values >= v) the lex rank
+// is  rank = sum_i [ G(x_{i-1}, r_i) - G(x_i, r_i) ],  r_i = k-1-i,  x_{-1} = 0.  Removing the element at
+// position p gives the parent (k-1 photons) with
+//     rank(parent) = rank - Q[p+1],   Q[j] = sum_{i<j} [ H(x_{i-1}, r_i) - H(x_i, r_i) ],  H(v, r) = C(m-v+r-1, r+1)
+// (Pascal's rule applied to the difference of the two rank sums), i.e. one prefix table per state.  A lane
+// walks ranks base + 32*it + lane: consecutive lanes hold consecutive children, so stores and most parent
+// gathers are coalesced; advancing by 32 re-derives only the trailing positions whose block the step leaves.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,16 +33,18 @@
 namespace lwb {
 
 constexpr int SLOS_THREADS = 256;
+constexpr int SLOS_ITERS = 8;  // children per lane
 
 struct SlosLayerArgs {
     const uint64_t* bin;    // binomial table (device, LWB_BIN_B stride)
     int m, k;               // modes, photons in the CHILD layer
     uint64_t S;             // number of child states
-    const double2* parent;  // layer k-1
-    double2* child;         // layer k
+    const double2* parent;  // layer k-1 (lex order)
+    void* child;            // layer k (lex order): double2 amplitudes, or double |a|^2 when write_probs
     const double2* U;       // m x m
     int in_mode;            // i_k
     const double* sqrt_tab; // sqrt_tab[c] = pow(c, 0.5) computed on the host (slos.py:121)
+    int write_probs;        // final layer only: store abs(a)**2 (slos.py:74) instead of the amplitude
 };
 
 // complex multiply exactly as CPython's complex_mul: (ac - bd) + (ad + bc)i, no fma
@@ -48,80 +55,123 @@ __device__ __forceinline__ double2 cmul_py(double2 a, double2 b) {
     return r;
 }
 
-template <int KMAX>
+// IDX = uint32_t when the layer (and every table entry) fits 32 bits, else uint64_t.
+template <int KMAX, typename IDX>
 __global__ void __launch_bounds__(SLOS_THREADS) slos_layer_kernel(SlosLayerArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // smem: binomials [m+k][k+1] u64, U column [m] double2, sqrt table [k+1]
     const int k = a.k, m = a.m;
-    const int bw = k + 1, bh = m + k;
-    uint64_t* sb = reinterpret_cast<uint64_t*>(smem_raw);
-    double2* ucol = reinterpret_cast<double2*>(sb + (((size_t)bh * bw + 1) & ~(size_t)1));  // keep 16-byte alignment
+    const int mv = m + 1;  // table width over v in [0, m]
+    // smem: ucol [m] double2 | sq [k+1] double | cnt[k][mv] | Gt[k][mv] | Ht[k][mv]   (rows indexed by r = rem)
+    double2* ucol = reinterpret_cast<double2*>(smem_raw);
     double* sq = reinterpret_cast<double*>(ucol + m);
-    for (int e = threadIdx.x; e < bh * bw; e += SLOS_THREADS) sb[e] = a.bin[(e / bw) * LWB_BIN_B + (e % bw)];
+    IDX* cnt = reinterpret_cast<IDX*>(sq + ((k + 2) & ~1));
+    IDX* Gt = cnt + k * mv;
+    IDX* Ht = Gt + k * mv;
     for (int e = threadIdx.x; e < m; e += SLOS_THREADS) ucol[e] = a.U[(size_t)e * m + a.in_mode];
     for (int e = threadIdx.x; e <= k; e += SLOS_THREADS) sq[e] = a.sqrt_tab[e];
+    for (int e = threadIdx.x; e < k * mv; e += SLOS_THREADS) {
+        const int r = e / mv, v = e - r * mv;
+        cnt[e] = (IDX)binom(a.bin, m - v + r - 1, r);      // lists of length r+1 over >= v that START with v
+        Gt[e] = (IDX)binom(a.bin, m - v + r, r + 1);       // all lists of length r+1 over values >= v
+        Ht[e] = (IDX)binom(a.bin, m - v + r - 1, r + 1);
+    }
     __syncthreads();
 
-    const uint64_t r = (uint64_t)blockIdx.x * SLOS_THREADS + threadIdx.x;
-    if (r >= a.S) return;
+    const uint64_t warp_base = ((uint64_t)blockIdx.x * (SLOS_THREADS / 32) + (threadIdx.x >> 5)) * (32ull * SLOS_ITERS);
+    const int lane = threadIdx.x & 31;
+    if (warp_base >= a.S) return;
 
-    // unrank (colex greedy) -> x[1..k] ascending, and A_i, B_i on the fly
-    int x[KMAX + 1];
-    uint64_t A[KMAX + 1], B[KMAX + 2];
-    {
-        uint64_t rem = r;
-        int y = m + k - 2;
+    int x[KMAX];
+    IDX Q[KMAX + 1];   // Q[j] = sum_{i<j} dq(i)
+    IDX O[KMAX];       // O[i] = offset of the state inside the block of states sharing x_0..x_{i-1}
+    IDX W[KMAX];       // W[i] = size of that block = G(x_{i-1}, r_i)
+    IDX rank = (IDX)(warp_base + lane);
+    int level = 0;     // positions >= level must be (re)derived from offset `off`
+    IDX off = rank;
+    Q[0] = 0;
+
+#pragma unroll 1
+    for (int it = 0; it < SLOS_ITERS; ++it) {
+        if ((uint64_t)rank >= a.S) break;
+        // ---- (re)derive positions >= level: lex unrank of `off` inside the block of the kept prefix ----
+        {
+            int prev = 0;
 #pragma unroll
-        for (int i = KMAX; i >= 1; --i) {
-            if (i <= k) {
-                while (sb[y * bw + i] > rem) --y;
-                const uint64_t c = sb[y * bw + i];
-                rem -= c;
-                x[i] = y - i + 1;
-                A[i] = c;
-                B[i] = (y >= 1) ? sb[(y - 1) * bw + (i - 1)] : (i == 1 ? 1 : 0);
-                y -= 1;
-                if (y < 0) y = 0;
+            for (int pos = 0; pos < KMAX; ++pos) {
+                if (pos < k) {
+                    if (pos >= level) {
+                        const int r = k - 1 - pos;
+                        W[pos] = Gt[r * mv + prev];
+                        O[pos] = off;
+                        int v = prev;
+                        if (r == 0) {
+                            v = prev + (int)off;  // one list per value
+                            off = 0;
+                        } else {
+                            const IDX* c = cnt + r * mv;
+                            IDX cv = c[v];
+                            while (off >= cv) { off -= cv; ++v; cv = c[v]; }
+                        }
+                        x[pos] = v;
+                        Q[pos + 1] = Q[pos] + (Ht[r * mv + prev] - Ht[r * mv + v]);
+                    }
+                    prev = x[pos];
+                }
             }
         }
-    }
-    // suffix sums of B (positions > p) and running prefix of A
-    uint64_t SB[KMAX + 2];
-    SB[k + 1 <= KMAX + 1 ? k + 1 : KMAX + 1] = 0;
+        // ---- gather parents: one term per distinct occupied mode, ascending (slos.py:98-103) ----
+        double2 acc = make_double2(0.0, 0.0);
+        bool first = true;
+        int run = 0;
 #pragma unroll
-    for (int i = KMAX; i >= 1; --i)
-        if (i <= k) SB[i] = SB[i + 1] + B[i];
-
-    double2 acc = make_double2(0.0, 0.0);
-    bool first = true;
-    uint64_t pa = 0;  // sum_{i<p} A_i
-    int run = 0;
-#pragma unroll
-    for (int p = 1; p <= KMAX; ++p) {
-        if (p <= k) {
-            run += 1;
-            const bool last_of_run = (p == k) || (x[p + 1] != x[p]);
-            if (last_of_run) {
-                // remove the element at position p (the last of its run): prefix uses A of positions < p
-                const uint64_t prank = pa + SB[p + 1];
-                const double2 v = a.parent[prank];
-                const double s = sq[run];
-                double2 t;
-                t.x = __dmul_rn(s, v.x);
-                t.y = __dmul_rn(s, v.y);
-                const double2 term = cmul_py(t, ucol[x[p]]);
-                if (first) { acc = term; first = false; }
-                else { acc.x = __dadd_rn(acc.x, term.x); acc.y = __dadd_rn(acc.y, term.y); }
-                run = 0;
+        for (int p = 0; p < KMAX; ++p) {
+            if (p < k) {
+                run += 1;
+                const bool last_of_run = (p == k - 1) || (x[p + 1 < KMAX ? p + 1 : p] != x[p]);
+                if (last_of_run) {
+                    const IDX prank = rank - Q[p + 1];
+                    double2 t = a.parent[prank];
+                    if (run > 1) {  // key[mode] ** 0.5 * value ; multiplying by sqrt(1) = 1.0 is exact, skip it
+                        const double s = sq[run];
+                        t.x = __dmul_rn(s, t.x);
+                        t.y = __dmul_rn(s, t.y);
+                    }
+                    const double2 term = cmul_py(t, ucol[x[p]]);
+                    if (first) { acc = term; first = false; }
+                    else { acc.x = __dadd_rn(acc.x, term.x); acc.y = __dadd_rn(acc.y, term.y); }
+                    run = 0;
+                }
             }
-            pa += A[p];
         }
+        if (a.write_probs) {
+            const double ab = hypot(acc.x, acc.y);  // abs(p) ** 2, slos.py:74
+            reinterpret_cast<double*>(a.child)[rank] = ab * ab;
+        } else {
+            reinterpret_cast<double2*>(a.child)[rank] = acc;
+        }
+        // ---- advance by 32: keep the longest prefix whose block still contains the new rank ----
+        rank += 32;
+        level = 0;
+        off = rank;
+#pragma unroll
+        for (int i = 1; i < KMAX; ++i) {
+            if (i < k) {
+                const IDX o = O[i] + 32;
+                if (o < W[i] && level == i - 1) {  // prefixes nest: level i is usable only if level i-1 was
+                    level = i;
+                    off = o;
+                }
+            }
+        }
+        // offsets of the kept levels move with the rank
+#pragma unroll
+        for (int i = 0; i < KMAX; ++i)
+            if (i < level) O[i] += 32;
     }
-    a.child[r] = acc;
 }
 
 // ---------------------------------------------------------------------------------------------
-// out[p] (p = SLOS / lexicographic position) = f(in[colex rank of that state]);
+// out[r] (r = colex / fock_basis rank) = f(in[SLOS-order position of that state]);
 // mode 0: copy complex amplitude; mode 1: |a|^2 from complex; mode 2: copy real.
 struct ReorderArgs {
     const uint64_t* bin;
@@ -133,46 +183,45 @@ struct ReorderArgs {
 };
 
 template <int KMAX>
-__global__ void __launch_bounds__(SLOS_THREADS) reorder_lex_kernel(ReorderArgs a) {
-    const uint64_t p = (uint64_t)blockIdx.x * SLOS_THREADS + threadIdx.x;
-    if (p >= a.S) return;
+__global__ void __launch_bounds__(SLOS_THREADS) reorder_to_colex_kernel(ReorderArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * SLOS_THREADS + threadIdx.x;
+    if (r >= a.S) return;
     int x[KMAX];
-    // lex_unrank with static indexing
-    {
-        uint64_t rank = p;
-        int prev = 0;
+    {   // colex greedy unrank with static indexing
+        uint64_t rem = r;
+        int y = a.m + a.n - 2;
 #pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-            if (i < a.n) {
-                const int rem = a.n - 1 - i;
-                int v = prev;
-                for (;;) {
-                    const uint64_t cnt = binom(a.bin, a.m - v + rem - 1, rem);
-                    if (rank < cnt) break;
-                    rank -= cnt;
-                    ++v;
-                }
-                x[i] = v;
-                prev = v;
+        for (int i = KMAX; i >= 1; --i) {
+            if (i <= a.n) {
+                while (binom(a.bin, y, i) > rem) --y;
+                rem -= binom(a.bin, y, i);
+                x[i - 1] = y - i + 1;
+                y -= 1;
             }
         }
     }
-    uint64_t r = 0;
+    uint64_t p = 0;  // lex rank
+    int prev = 0;
 #pragma unroll
-    for (int i = 1; i <= KMAX; ++i)
-        if (i <= a.n) r += binom(a.bin, x[i - 1] + i - 1, i);
+    for (int i = 0; i < KMAX; ++i) {
+        if (i < a.n) {
+            const int rem = a.n - 1 - i;
+            p += binom(a.bin, a.m - prev + rem, rem + 1) - binom(a.bin, a.m - x[i] + rem, rem + 1);
+            prev = x[i];
+        }
+    }
     if (a.mode == 0) {
-        reinterpret_cast<double2*>(a.out)[p] = reinterpret_cast<const double2*>(a.in)[r];
+        reinterpret_cast<double2*>(a.out)[r] = reinterpret_cast<const double2*>(a.in)[p];
     } else if (a.mode == 1) {
-        const double2 v = reinterpret_cast<const double2*>(a.in)[r];
-        const double ab = hypot(v.x, v.y);  // abs(p) ** 2, slos.py:74
-        a.out[p] = ab * ab;
+        const double2 v = reinterpret_cast<const double2*>(a.in)[p];
+        const double ab = hypot(v.x, v.y);
+        a.out[r] = ab * ab;
     } else {
-        a.out[p] = a.in[r];
+        a.out[r] = a.in[p];
     }
 }
 
-// |a|^2 in place order (colex): probs[r] = hypot(re, im)^2
+// |a|^2, same order: probs[r] = hypot(re, im)^2
 static __global__ void abs2_kernel(const double2* __restrict__ amps, uint64_t S, double* __restrict__ probs) {
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= S) return;
