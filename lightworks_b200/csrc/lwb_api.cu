@@ -593,25 +593,33 @@ static int launch_kmax(lwb_handle h, int n, uint64_t threads_needed, size_t smem
     return 0;
 }
 
-template <typename IDX>
+typedef void (*SlosFn)(SlosLayerArgs);
+template <int K>
+struct SlosTable {
+    static void fill(SlosFn (*t)[2]) {
+        t[K][0] = slos_layer_kernel<K, uint32_t>;
+        t[K][1] = slos_layer_kernel<K, uint64_t>;
+        SlosTable<K - 1>::fill(t);
+    }
+};
+template <>
+struct SlosTable<0> {
+    static void fill(SlosFn (*)[2]) {}
+};
+static SlosFn g_slos[LWB_MAX_PHOTONS + 1][2];
+static std::once_flag g_slos_once;
+
 static int launch_slos_layer(lwb_handle h, const SlosLayerArgs& a) {
+    std::call_once(g_slos_once, [] { SlosTable<LWB_MAX_PHOTONS>::fill(g_slos); });
     const int k = a.k, m = a.m;
-    const size_t smem = (size_t)m * 16 + (size_t)((k + 2) & ~1) * 8 + 3 * (size_t)k * (m + 1) * sizeof(IDX);
+    const int wide = a.S >= (1ull << 32) ? 1 : 0;
+    const size_t isz = wide ? 8 : 4;
+    const size_t smem = (size_t)m * 16 + (size_t)((k + 2) & ~1) * 8 + 3 * (size_t)k * (m + 1) * isz;
     const uint64_t warps = (a.S + 32ull * SLOS_ITERS - 1) / (32ull * SLOS_ITERS);
     const unsigned grid = (unsigned)((warps + SLOS_THREADS / 32 - 1) / (SLOS_THREADS / 32));
-#define LWB_GO(KM)                                                                                         \
-    do {                                                                                                   \
-        auto fn = slos_layer_kernel<KM, IDX>;                                                              \
-        if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        fn<<<grid, SLOS_THREADS, smem, h->stream>>>(a);                                                    \
-    } while (0)
-    if (k <= 4) LWB_GO(4);
-    else if (k <= 8) LWB_GO(8);
-    else if (k <= 12) LWB_GO(12);
-    else if (k <= 16) LWB_GO(16);
-    else if (k <= 24) LWB_GO(24);
-    else LWB_GO(40);
-#undef LWB_GO
+    SlosFn fn = g_slos[k][wide];
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<grid, SLOS_THREADS, smem, h->stream>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
@@ -649,8 +657,7 @@ static int slos_layers(lwb_handle h, const double* d_U, int m, const uint8_t* in
         a.U = (const double2*)d_U; a.in_mode = modes[k - 1];
         a.sqrt_tab = (const double*)h->bSmall.p + 2;
         a.write_probs = (k == n) ? final_probs : 0;
-        if (a.S < (1ull << 32)) CK(launch_slos_layer<uint32_t>(h, a));
-        else CK(launch_slos_layer<uint64_t>(h, a));
+        CK(launch_slos_layer(h, a));
     }
     return 0;
 }

@@ -33,7 +33,13 @@
 namespace lwb {
 
 constexpr int SLOS_THREADS = 256;
-constexpr int SLOS_ITERS = 8;  // children per lane
+#ifndef LWB_SLOS_ITERS
+#define LWB_SLOS_ITERS 16
+#endif
+#ifndef LWB_SLOS_MINB
+#define LWB_SLOS_MINB 4
+#endif
+constexpr int SLOS_ITERS = LWB_SLOS_ITERS;  // children per lane
 
 struct SlosLayerArgs {
     const uint64_t* bin;    // binomial table (device, LWB_BIN_B stride)
@@ -55,21 +61,22 @@ __device__ __forceinline__ double2 cmul_py(double2 a, double2 b) {
     return r;
 }
 
+// K = photons in the child layer (exact: every loop bound and table row is static);
 // IDX = uint32_t when the layer (and every table entry) fits 32 bits, else uint64_t.
-template <int KMAX, typename IDX>
-__global__ void __launch_bounds__(SLOS_THREADS) slos_layer_kernel(SlosLayerArgs a) {
+template <int K, typename IDX>
+__global__ void __launch_bounds__(SLOS_THREADS, LWB_SLOS_MINB) slos_layer_kernel(SlosLayerArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int k = a.k, m = a.m;
+    const int m = a.m;
     const int mv = m + 1;  // table width over v in [0, m]
-    // smem: ucol [m] double2 | sq [k+1] double | cnt[k][mv] | Gt[k][mv] | Ht[k][mv]   (rows indexed by r = rem)
+    // smem: ucol [m] double2 | sq [K+1] double | cnt[K][mv] | Gt[K][mv] | Ht[K][mv]   (rows indexed by r = rem)
     double2* ucol = reinterpret_cast<double2*>(smem_raw);
     double* sq = reinterpret_cast<double*>(ucol + m);
-    IDX* cnt = reinterpret_cast<IDX*>(sq + ((k + 2) & ~1));
-    IDX* Gt = cnt + k * mv;
-    IDX* Ht = Gt + k * mv;
+    IDX* cnt = reinterpret_cast<IDX*>(sq + ((K + 2) & ~1));
+    IDX* Gt = cnt + K * mv;
+    IDX* Ht = Gt + K * mv;
     for (int e = threadIdx.x; e < m; e += SLOS_THREADS) ucol[e] = a.U[(size_t)e * m + a.in_mode];
-    for (int e = threadIdx.x; e <= k; e += SLOS_THREADS) sq[e] = a.sqrt_tab[e];
-    for (int e = threadIdx.x; e < k * mv; e += SLOS_THREADS) {
+    for (int e = threadIdx.x; e <= K; e += SLOS_THREADS) sq[e] = a.sqrt_tab[e];
+    for (int e = threadIdx.x; e < K * mv; e += SLOS_THREADS) {
         const int r = e / mv, v = e - r * mv;
         cnt[e] = (IDX)binom(a.bin, m - v + r - 1, r);      // lists of length r+1 over >= v that START with v
         Gt[e] = (IDX)binom(a.bin, m - v + r, r + 1);       // all lists of length r+1 over values >= v
@@ -81,12 +88,12 @@ __global__ void __launch_bounds__(SLOS_THREADS) slos_layer_kernel(SlosLayerArgs 
     const int lane = threadIdx.x & 31;
     if (warp_base >= a.S) return;
 
-    int x[KMAX];
-    IDX Q[KMAX + 1];   // Q[j] = sum_{i<j} dq(i)
-    IDX O[KMAX];       // O[i] = offset of the state inside the block of states sharing x_0..x_{i-1}
-    IDX W[KMAX];       // W[i] = size of that block = G(x_{i-1}, r_i)
+    int x[K];
+    IDX Q[K + 1];   // Q[j] = sum_{i<j} dq(i)
+    IDX O[K];       // O[i] = offset of the state inside the block of states sharing x_0..x_{i-1}
+    IDX W[K];       // W[i] = size of that block = G(x_{i-1}, r_i)
     IDX rank = (IDX)(warp_base + lane);
-    int level = 0;     // positions >= level must be (re)derived from offset `off`
+    int level = 0;  // positions >= level must be (re)derived from offset `off`
     IDX off = rank;
     Q[0] = 0;
 
@@ -97,50 +104,48 @@ __global__ void __launch_bounds__(SLOS_THREADS) slos_layer_kernel(SlosLayerArgs 
         {
             int prev = 0;
 #pragma unroll
-            for (int pos = 0; pos < KMAX; ++pos) {
-                if (pos < k) {
-                    if (pos >= level) {
-                        const int r = k - 1 - pos;
-                        W[pos] = Gt[r * mv + prev];
-                        O[pos] = off;
-                        int v = prev;
-                        if (r == 0) {
-                            v = prev + (int)off;  // one list per value
-                            off = 0;
-                        } else {
-                            const IDX* c = cnt + r * mv;
-                            IDX cv = c[v];
-                            while (off >= cv) { off -= cv; ++v; cv = c[v]; }
-                        }
-                        x[pos] = v;
-                        Q[pos + 1] = Q[pos] + (Ht[r * mv + prev] - Ht[r * mv + v]);
+            for (int pos = 0; pos < K; ++pos) {
+                if (pos >= level) {
+                    const int r = K - 1 - pos;  // static after unrolling
+                    W[pos] = Gt[r * mv + prev];
+                    O[pos] = off;
+                    int v = prev;
+                    if (r == 0) {
+                        v = prev + (int)off;  // one list per value
+                        off = 0;
+                    } else {
+                        const IDX* c = cnt + r * mv;
+                        IDX cv = c[v];
+                        while (off >= cv) { off -= cv; ++v; cv = c[v]; }
                     }
-                    prev = x[pos];
+                    x[pos] = v;
+                    Q[pos + 1] = Q[pos] + (Ht[r * mv + prev] - Ht[r * mv + v]);
                 }
+                prev = x[pos];
             }
         }
         // ---- gather parents: one term per distinct occupied mode, ascending (slos.py:98-103) ----
         double2 acc = make_double2(0.0, 0.0);
-        bool first = true;
         int run = 0;
 #pragma unroll
-        for (int p = 0; p < KMAX; ++p) {
-            if (p < k) {
-                run += 1;
-                const bool last_of_run = (p == k - 1) || (x[p + 1 < KMAX ? p + 1 : p] != x[p]);
-                if (last_of_run) {
-                    const IDX prank = rank - Q[p + 1];
-                    double2 t = a.parent[prank];
-                    if (run > 1) {  // key[mode] ** 0.5 * value ; multiplying by sqrt(1) = 1.0 is exact, skip it
-                        const double s = sq[run];
-                        t.x = __dmul_rn(s, t.x);
-                        t.y = __dmul_rn(s, t.y);
-                    }
-                    const double2 term = cmul_py(t, ucol[x[p]]);
-                    if (first) { acc = term; first = false; }
-                    else { acc.x = __dadd_rn(acc.x, term.x); acc.y = __dadd_rn(acc.y, term.y); }
-                    run = 0;
+        for (int p = 0; p < K; ++p) {
+            run += 1;
+            bool last_of_run = true;
+            if (p + 1 < K) last_of_run = x[p + 1 < K ? p + 1 : p] != x[p];
+            if (last_of_run) {
+                const IDX prank = rank - Q[p + 1];
+                double2 t = a.parent[prank];
+                if (run > 1) {  // key[mode] ** 0.5 * value ; multiplying by sqrt(1) = 1.0 is exact, skip it
+                    const double s = sq[run];
+                    t.x = __dmul_rn(s, t.x);
+                    t.y = __dmul_rn(s, t.y);
                 }
+                const double2 term = cmul_py(t, ucol[x[p]]);
+                // the first term is added to +0.0: x + 0.0 == x for every x except -0.0, and a -0.0 first
+                // term can only differ from the reference (which assigns it) in the sign of an exact zero
+                acc.x = __dadd_rn(acc.x, term.x);
+                acc.y = __dadd_rn(acc.y, term.y);
+                run = 0;
             }
         }
         if (a.write_probs) {
@@ -154,19 +159,16 @@ __global__ void __launch_bounds__(SLOS_THREADS) slos_layer_kernel(SlosLayerArgs 
         level = 0;
         off = rank;
 #pragma unroll
-        for (int i = 1; i < KMAX; ++i) {
-            if (i < k) {
-                const IDX o = O[i] + 32;
-                if (o < W[i] && level == i - 1) {  // prefixes nest: level i is usable only if level i-1 was
-                    level = i;
-                    off = o;
-                }
+        for (int i = 1; i < K; ++i) {
+            const IDX o = O[i] + 32;
+            if (o < W[i] && level == i - 1) {  // blocks nest: level i is usable only if level i-1 is
+                level = i;
+                off = o;
             }
         }
-        // offsets of the kept levels move with the rank
 #pragma unroll
-        for (int i = 0; i < KMAX; ++i)
-            if (i < level) O[i] += 32;
+        for (int i = 0; i < K; ++i)
+            if (i < level) O[i] += 32;  // offsets of the kept levels move with the rank
     }
 }
 
