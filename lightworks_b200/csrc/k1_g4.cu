@@ -1,12 +1,15 @@
 // generated instantiation unit: K1 variants (N, LOG_L) compiled in this translation unit
+// (first entry per N = default; the rest are selectable with lwb_set_tuning for sweeps)
 #include "variants.h"
 #include "perm_kernels.cuh"
 namespace lwb {
 static const K1Variant table[] = {
-    LWB_K1_ENTRY(18, 5),
-    LWB_K1_ENTRY(19, 5),
-    LWB_K1_ENTRY(20, 5),
-    LWB_K1_ENTRY(20, 4),
+    LWB_K1_ENTRY(15, 4),
+    LWB_K1_ENTRY(16, 5),
+    LWB_K1_ENTRY(17, 5),
+    LWB_K1_ENTRY(15, 5),
+    LWB_K1_ENTRY(16, 3),
+    LWB_K1_ENTRY(16, 4),
 };
 const K1Variant* k1_g4_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -1,10 +1,15 @@
 // generated instantiation unit: K1 variants (N, LOG_L) compiled in this translation unit
+// (first entry per N = default; the rest are selectable with lwb_set_tuning for sweeps)
 #include "variants.h"
 #include "perm_kernels.cuh"
 namespace lwb {
 static const K1Variant table[] = {
-    LWB_K1_ENTRY(21, 5),
-    LWB_K1_ENTRY(22, 5),
+    LWB_K1_ENTRY(18, 5),
+    LWB_K1_ENTRY(19, 5),
+    LWB_K1_ENTRY(20, 5),
+    LWB_K1_ENTRY(18, 4),
+    LWB_K1_ENTRY(20, 3),
+    LWB_K1_ENTRY(20, 4),
 };
 const K1Variant* k1_g5_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -4,13 +4,8 @@
 #include "perm_kernels.cuh"
 namespace lwb {
 static const K1Variant table[] = {
-    LWB_K1_ENTRY(9, 1),
-    LWB_K1_ENTRY(10, 1),
-    LWB_K1_ENTRY(9, 0),
-    LWB_K1_ENTRY(9, 2),
-    LWB_K1_ENTRY(10, 0),
-    LWB_K1_ENTRY(10, 2),
-    LWB_K1_ENTRY(10, 3),
+    LWB_K1_ENTRY(23, 5),
+    LWB_K1_ENTRY(24, 5),
 };
-const K1Variant* k1_g1_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
+const K1Variant* k1_g7_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -20,7 +20,7 @@ constexpr int K1_THREADS = 256;
 #define LWB_U(N) ((N) <= 14 ? 4 : 3)
 #endif
 #ifndef LWB_U2
-#define LWB_U2 2  /* K2 */
+#define LWB_U2(N) ((N) >= 27 ? 1 : 2)  /* K2: measured best on B200 (register pressure grows with n) */
 #endif
 #ifndef LWB_MINB
 #define LWB_MINB 1
@@ -240,7 +240,7 @@ struct K2Shape {
     static constexpr int C0 = N - 21;
     static constexpr int CC = C0 < 3 ? 3 : (C0 > 7 ? 7 : C0);
     static constexpr int C = CC > N - 1 ? (N - 1 < 1 ? 1 : N - 1) : CC;
-    static constexpr int U = C < LWB_U2 ? C : LWB_U2;
+    static constexpr int U = C < LWB_U2(N) ? C : LWB_U2(N);
 };
 
 template <int N, typename T>

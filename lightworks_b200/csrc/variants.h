@@ -30,11 +30,12 @@ const K1Variant* k1_g3_table(int* count);
 const K1Variant* k1_g4_table(int* count);
 const K1Variant* k1_g5_table(int* count);
 const K1Variant* k1_g6_table(int* count);
+const K1Variant* k1_g7_table(int* count);
 const K2Variant* k2_g0_table(int* count);
 const K2Variant* k2_g1_table(int* count);
 const K2Variant* k2_g2_table(int* count);
 const K2Variant* k2_g3_table(int* count);
-#define LWB_K1_GROUPS {k1_g0_table, k1_g1_table, k1_g2_table, k1_g3_table, k1_g4_table, k1_g5_table, k1_g6_table}
+#define LWB_K1_GROUPS {k1_g0_table, k1_g1_table, k1_g2_table, k1_g3_table, k1_g4_table, k1_g5_table, k1_g6_table, k1_g7_table}
 #define LWB_K2_GROUPS {k2_g0_table, k2_g1_table, k2_g2_table, k2_g3_table}
 
 }  // namespace lwb

@@ -56,14 +56,14 @@ with torch.cuda.stream(stream):
         S = L.fock_count(24, 10)
         cnt = S // 8
         probs = torch.empty(cnt, dtype=torch.float64, device="cuda")
-        for ll in (3, 4, 5):
+        for ll in (2, 3, 4):
             L.set_tuning(10, ll)
             t = time_fn(lambda: ctx.perm_basis_probs_dev(U, 24, ins, 10, 0, cnt, probs), reps=3)
             tf = cnt * 2.0 ** 9 * 76 / t
             print(f"[{tag}] C3/8 log_l={ll} cnt={cnt} t={t*1e3:.2f} ms {cnt/t:.3e} probs/s {tf/1e12:.2f} TF frac={tf/PEAK:.3f}", flush=True)
         L.set_tuning(10, -1)
         U60 = O.random_unitary(60, 5)
-        for n in [20, 24, 28, 30]:
+        for n in [20, 22, 24, 26, 28, 30, 32]:
             A = torch.from_numpy(U60[:n, :n].copy()).cuda()
             o2 = torch.empty(2, dtype=torch.float64, device="cuda")
             t = time_fn(lambda: ctx.perm_single_dev(A, n, o2), reps=3)
