@@ -344,6 +344,25 @@ def main() -> int:  # noqa: PLR0915
         "gpu_launches": int(launches), "clocks": clocks, "wall_ms_timed_region": dev_wall,
     }
 
+    if world > 1 and not args.no_extras:
+        # C5: one 28 x 28 permanent of the 60-mode Haar unitary (seed 5), Gray-code space sliced over the ranks,
+        # partial sums combined by a 16-byte all-reduce
+        n5 = 28
+        with torch.cuda.stream(stream):
+            A5 = torch.from_numpy(O.random_unitary(60, 5)[:n5, :n5].copy()).cuda()  # noqa: N806
+            o5 = torch.zeros(2, dtype=torch.float64, device="cuda")
+
+        def single_step():
+            ctx.perm_single_dev(A5, n5, o5, slice_=rank, n_slices=world)
+            dist.all_reduce(o5)
+
+        with torch.cuda.stream(stream):
+            single_step()
+        ms5, _, _ = timed(single_step, 5)
+        ms5 = max_over_ranks(ms5) / 5
+        line["extra"] = {"single_perm_n28_sharded": {"ms": ms5, "permanents_per_s": 1e3 / ms5,
+                                                      "fp64_frac_per_gpu": flops_per_perm(n5) / (ms5 * 1e-3) / peak / world,
+                                                      "value": [float(o5[0]), float(o5[1])]}}
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         line["cpu_baseline"] = cpu_port_baseline(U, ins, args.cpu_sample, threads)
@@ -357,9 +376,15 @@ def main() -> int:  # noqa: PLR0915
 
 
 def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
-    """Other rows of the metric (reported, not the headline): SLOS probabilities/s on the same
-    distribution, batched n x n permanents/s for n = 12, 16, 20 and single large permanents."""
+    """Other rows of the metric (reported, not the headline): SLOS probabilities/s on the same distribution
+    with its HBM roofline, batched n x n permanents/s (complex128 n = 12, 16, 20; complex64 n = 12), the C4
+    noise-model hot path (all 255 photon-subset inputs of 8 photons in 16 modes) and single large permanents."""
     out = {}
+    hbm = None
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    except Exception:
+        hbm = 6650.0  # B200_PROFILING.md fallback
 
     def t_ms(fn, reps=3):
         with torch.cuda.stream(stream):
@@ -375,26 +400,48 @@ def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
                 ts.append(e0.elapsed_time(e1))
         return min(ts)
 
+    from math import comb
+
     S = _lib.fock_count(M, N_PH)  # noqa: N806
     ins = [1] * N_PH + [0] * (M - N_PH)
     with torch.cuda.stream(stream):
         d_p = torch.empty(S, dtype=torch.float64, device="cuda")
     ms = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1))
-    from math import comb
-
+    # algorithmic bytes: every layer reads its parent once and writes itself once (the last layer
+    # writes 8-byte probabilities)
     slos_bytes = sum(16 * (comb(M + k - 2, k - 1) + comb(M + k - 1, k)) for k in range(1, N_PH + 1))
-    out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms, "algorithmic_GBps": slos_bytes / (ms * 1e-3) / 1e9,
-                      "note": "SLOS backend, same distribution, SLOS dict order, all layers + reorder"}
+    out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms,
+                      "roofline": {"bound": "hbm", "achieved": slos_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                   "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes},
+                      "note": "SLOS backend, same distribution in SLOS dict order, all 10 layers"}
     del d_p
-    for n in (12, 16, 20):
+    for n, dt, name in ((12, _lib.LWB_C128, "c128"), (16, _lib.LWB_C128, "c128"), (20, _lib.LWB_C128, "c128"),
+                        (12, _lib.LWB_C64, "c64")):
         B = int(max(2e11 / flops_per_perm(n), 148 * 64))  # noqa: N806
         with torch.cuda.stream(stream):
             A = torch.randn(B, n, n, 2, dtype=torch.float64, device="cuda") / np.sqrt(n)  # noqa: N806
             o = torch.empty(B, 2, dtype=torch.float64, device="cuda")
-        ms = t_ms(lambda: ctx.perm_matrices_dev(A, B, n, o))
-        out[f"batched_perm_n{n}"] = {"permanents_per_s": B / (ms * 1e-3), "batch": B, "ms": ms,
-                                     "fp64_frac": B * flops_per_perm(n) / (ms * 1e-3) / peak}
+        ms = t_ms(lambda: ctx.perm_matrices_dev(A, B, n, o, dt))
+        rec = {"permanents_per_s": B / (ms * 1e-3), "batch": B, "ms": ms}
+        if dt == _lib.LWB_C128:
+            rec["fp64_frac"] = B * flops_per_perm(n) / (ms * 1e-3) / peak
+        out[f"batched_perm_n{n}_{name}"] = rec
         del A, o
+    # C4 hot path: every non-empty subset of the 8 input photons (255 inputs), 16 modes, full output basis each
+    U16 = torch.from_numpy(O.random_unitary(16, 4)).cuda()  # noqa: N806
+    subsets = [[(b >> i) & 1 for i in range(8)] + [0] * 8 for b in range(1, 256)]
+    with torch.cuda.stream(stream):
+        d_sub = [torch.tensor(sb, dtype=torch.uint8, device="cuda") for sb in subsets]
+        d_buf = torch.empty(_lib.fock_count(16, 8), dtype=torch.float64, device="cuda")
+    counts = [_lib.fock_count(16, sum(sb)) for sb in subsets]
+
+    def c4():
+        for sb, dsb, c in zip(subsets, d_sub, counts):
+            ctx.perm_basis_probs_dev(U16, 16, dsb, sum(sb), 0, c, d_buf)
+
+    ms = t_ms(c4)
+    out["c4_hot_path"] = {"permanents_per_s": sum(counts) / (ms * 1e-3), "permanents": sum(counts), "launches": 255, "ms": ms,
+                          "note": "255 photon-subset inputs of |1^8,0^8>, 16 modes (SURVEY.md 8d C4), device-resident"}
     U60 = O.random_unitary(60, 5)  # noqa: N806
     for n in (24, 28):
         with torch.cuda.stream(stream):
