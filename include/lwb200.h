@@ -54,6 +54,10 @@ int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, 
 /* Kernel variant selection for n-photon permanents: lanes per permanent = 2^log_l,
  * min resident blocks per SM = minb.  Negative values restore the default. */
 int lwb_set_tuning(int n, int log_l, int minb);
+/* Process-wide options.  "multiplicity_aware" (default 1): full-basis probability ranges use the
+ * multiplicity-aware Glynn walk (prod(s_i+1)/2 terms for an output with occupations s_i) instead of
+ * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel. */
+int lwb_set_option(const char* name, int value);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int lwb_launch_count(lwb_handle h, uint64_t* count);
 

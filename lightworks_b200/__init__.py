@@ -16,6 +16,7 @@ from ._lib import (  # noqa: F401
     fock_count,
     fock_rank,
     fock_unrank,
+    set_option,
     set_tuning,
     slos_rank,
     slos_unrank,

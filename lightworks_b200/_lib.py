@@ -43,6 +43,7 @@ SIGNATURES = {
     "lwb_synchronize": (_i, [_vp]),
     "lwb_device_info": (_i, [_vp, _pi, _pi, C.c_char_p, _i]),
     "lwb_set_tuning": (_i, [_i, _i, _i]),
+    "lwb_set_option": (_i, [C.c_char_p, _i]),
     "lwb_launch_count": (_i, [_vp, _pu64]),
     "lwb_fock_count": (_i, [_i, _i, _pu64]),
     "lwb_fock_rank": (_i, [_i, _vp, _pu64]),
@@ -356,6 +357,10 @@ def _dev_methods():
 
 
 _dev_methods()
+
+
+def set_option(name: str, value: int):
+    check(cdll().lwb_set_option(name.encode(), int(value)))
 
 
 def set_tuning(n: int, log_l: int = -1, minb: int = -1):

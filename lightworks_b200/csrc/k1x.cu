@@ -1,0 +1,494 @@
+// k1x.cu -- multiplicity-aware batched permanents (see k1x.h for the formula and the plan).
+#include "k1x.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+#include "../../include/lwb200.h"
+#include "fock.cuh"
+#include "glynn.cuh"
+
+namespace lwb {
+
+constexpr int K1X_THREADS = 256;
+constexpr int K1X_MAX_N = 16;       // kernels instantiated for 2 <= n <= 16
+constexpr int K1X_CL_THREADS = 1024;  // one state per thread in the bucketing passes
+constexpr int K1X_MAX_TYPES = 256;    // partitions of n: p(16) = 231
+
+struct TypeMeta {
+    int d;         // distinct rows
+    int T;         // terms of the walk
+    int prog_off;  // first Step of this type in the program array
+    int factor;    // 2 when the v -> s-v symmetry halves the sum, else 1
+    int s[K1X_MAX_N];  // multiplicities, descending
+};
+struct Step {
+    double coef;  // (-1)^{sum v} prod C(s_i, v_i) of the tuple BEFORE the transition
+    int slot;     // row slot whose v changes after this term (unused for the last term)
+    int dir;      // +1 / -1
+};
+struct BlockWork {
+    int type;
+    uint32_t begin, end;  // range of bucket entries
+};
+
+// ---- type key: parts >= 2 of the partition, descending, 5 bits each ------------------------------------
+__host__ __device__ inline uint64_t pack_key(const int* parts_desc, int count) {
+    uint64_t k = 0;
+    for (int i = 0; i < count; ++i) k |= (uint64_t)parts_desc[i] << (5 * i);
+    return k;
+}
+
+// multiplicity pattern of an ascending mode list -> key (parts >= 2 sorted descending)
+template <int NMAX>
+__device__ __forceinline__ uint64_t key_of_modes(const int* x, int n) {
+    int parts[NMAX / 2 + 1];
+    int np = 0, run = 1;
+    for (int i = 1; i <= n; ++i) {
+        if (i < n && x[i] == x[i - 1]) { ++run; continue; }
+        if (run >= 2) {  // insertion into the descending list
+            int p = np++;
+            while (p > 0 && parts[p - 1] < run) { parts[p] = parts[p - 1]; --p; }
+            parts[p] = run;
+        }
+        run = 1;
+    }
+    return pack_key(parts, np);
+}
+
+__device__ __forceinline__ int find_type(const uint64_t* keys, int n_types, uint64_t key) {
+    int lo = 0, hi = n_types - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+struct ClassifyArgs {
+    const uint64_t* bin;
+    int m, n;
+    uint64_t r0, cnt;
+    const uint64_t* keys;      // sorted
+    const int* key_type;       // type id of keys[i]
+    int n_types;
+    uint32_t nb;               // number of classify blocks
+    uint32_t* H;               // [n_types][nb]: pass 1 writes per-block counts; scanned in place to exclusive prefixes
+    const uint32_t* offsets;   // pass 2: first bucket slot of every type
+    uint32_t* bucket;          // pass 2 output
+    int fill;
+};
+
+// Stable bucketing of the rank range by multiplicity pattern, two passes over the same layout (thread <-> one
+// rank).  Pass 1 (fill = 0): per-block counts H[type][block].  After the per-type exclusive scan of H, pass 2
+// (fill = 1) writes every state's range-relative index to bucket[offsets[type] + H[type][block] + (rank of the
+// state among the block's states of that type)], so every bucket lists its states in ascending rank order:
+// neighbouring lanes of the permanent kernel then hold nearly identical states and their row reads coalesce
+// into shared-memory broadcasts.
+template <int NMAX>
+__global__ void __launch_bounds__(K1X_CL_THREADS) k1x_classify_kernel(ClassifyArgs a) {
+    __shared__ unsigned short whist[K1X_CL_THREADS / 32][K1X_MAX_TYPES];
+    for (int e = threadIdx.x; e < (K1X_CL_THREADS / 32) * K1X_MAX_TYPES; e += K1X_CL_THREADS)
+        (&whist[0][0])[e] = 0;
+    __syncthreads();
+    const uint64_t k = (uint64_t)blockIdx.x * K1X_CL_THREADS + threadIdx.x;
+    const bool valid = k < a.cnt;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int t = K1X_MAX_TYPES + lane;  // invalid lanes never match anybody
+    if (valid) {
+        int x[NMAX];
+        colex_unrank(a.bin, a.r0 + k, a.n, a.m, x);
+        t = a.key_type[find_type(a.keys, a.n_types, key_of_modes<NMAX>(x, a.n))];
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, t);
+    const int in_warp = __popc(peers & ((1u << lane) - 1u));
+    if (valid && in_warp == 0) whist[w][t] = (unsigned short)__popc(peers);
+    __syncthreads();
+    if (!a.fill) {
+        for (int ty = threadIdx.x; ty < a.n_types; ty += K1X_CL_THREADS) {
+            unsigned int tot = 0;
+            for (int ww = 0; ww < K1X_CL_THREADS / 32; ++ww) tot += whist[ww][ty];
+            a.H[(size_t)ty * a.nb + blockIdx.x] = tot;
+        }
+        return;
+    }
+    if (valid) {
+        unsigned int pos = a.offsets[t] + a.H[(size_t)t * a.nb + blockIdx.x] + in_warp;
+        for (int ww = 0; ww < w; ++ww) pos += whist[ww][t];
+        a.bucket[pos] = (uint32_t)k;
+    }
+}
+
+// In-place exclusive scan of every row H[type][0..nb) and the row totals; one block per type.
+__global__ void __launch_bounds__(1024) k1x_scan_kernel(uint32_t* H, uint32_t nb, unsigned int* totals) {
+    __shared__ unsigned int part[1024];
+    uint32_t* row = H + (size_t)blockIdx.x * nb;
+    const uint32_t chunk = (nb + 1023) / 1024;
+    const uint32_t b = threadIdx.x * chunk, e = min(nb, b + chunk);
+    unsigned int sum = 0;
+    for (uint32_t i = b; i < e; ++i) sum += row[i];
+    part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {  // Hillis-Steele inclusive scan of the 1024 chunk sums
+        unsigned int v = threadIdx.x >= off ? part[threadIdx.x - off] : 0;
+        __syncthreads();
+        part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    unsigned int run = part[threadIdx.x] - sum;  // exclusive prefix of this chunk
+    for (uint32_t i = b; i < e; ++i) {
+        const unsigned int v = row[i];
+        row[i] = run;
+        run += v;
+    }
+    if (threadIdx.x == 1023) totals[blockIdx.x] = part[1023];
+}
+
+struct K1xArgs {
+    const uint64_t* bin;
+    const double2* U;
+    int m;
+    const uint8_t* in_state;
+    uint64_t r0;
+    const TypeMeta* meta;
+    const Step* prog;
+    const BlockWork* work;
+    const uint32_t* bucket;
+    double* probs;
+};
+
+template <int N>
+__global__ void __launch_bounds__(K1X_THREADS) k1x_kernel(K1xArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NP = N | 1;  // odd row stride (in 16-byte units): lanes reading different rows spread over the banks
+    double2* Vs = reinterpret_cast<double2*>(smem_raw);                  // [m][NP]
+    int* srow = reinterpret_cast<int*>(Vs + (size_t)a.m * NP);           // [N][K1X_THREADS] row offsets per slot
+    __shared__ int incol[N];
+    __shared__ double fin_s;
+    __shared__ TypeMeta tm;
+    const int tid = threadIdx.x;
+    const int m = a.m;
+    const BlockWork bw = a.work[blockIdx.x];
+    if (tid == 0) {
+        int c = 0;
+        double f = 1.0;
+        for (int i = 0; i < m; ++i)
+            for (int k = 0; k < a.in_state[i]; ++k) {
+                if (c < N) incol[c] = i;
+                ++c;
+                f *= (double)(k + 1);
+            }
+        fin_s = f;
+        tm = a.meta[bw.type];
+    }
+    __syncthreads();
+    for (int e = tid; e < m * N; e += K1X_THREADS) {
+        const int r = e / N, c = e - r * N;
+        Vs[r * NP + c] = a.U[(size_t)r * m + incol[c]];
+    }
+    __syncthreads();
+    const uint32_t item = bw.begin + tid;
+    if (item >= bw.end) return;
+    const uint32_t k = a.bucket[item];
+
+    // this thread's output state -> distinct modes ordered by decreasing multiplicity (= the type's slot order)
+    const int d = tm.d;
+    double fout = 1.0;
+    {
+        int x[N];
+        colex_unrank(a.bin, a.r0 + k, N, m, x);
+        int mode[N], mult[N];
+        int nd = 0, run = 1;
+        for (int i = 1; i <= N; ++i) {
+            if (i < N && x[i] == x[i - 1]) { ++run; fout *= (double)run; continue; }
+            int p = nd++;
+            while (p > 0 && mult[p - 1] < run) { mult[p] = mult[p - 1]; mode[p] = mode[p - 1]; --p; }
+            mult[p] = run;
+            mode[p] = x[i - 1];
+            run = 1;
+        }
+        for (int sl = 0; sl < nd; ++sl) srow[sl * K1X_THREADS + tid] = mode[sl] * NP;
+    }
+
+    // start tuple v = 0:  w_j = 1/2 sum_i s_i a_{r_i j}
+    double wr[N], wi[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { wr[j] = 0.0; wi[j] = 0.0; }
+    for (int sl = 0; sl < d; ++sl) {
+        const double c = 0.5 * (double)tm.s[sl];
+        const double2* row = Vs + srow[sl * K1X_THREADS + tid];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double2 v = lds_c(row, j);
+            wr[j] = fma(c, v.x, wr[j]);
+            wi[j] = fma(c, v.y, wi[j]);
+        }
+    }
+    const Step* prog = a.prog + tm.prog_off;
+    const int T = tm.T;
+    double sr = 0.0, si = 0.0;
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        const Step st = prog[t];  // same address for every lane of the block: one broadcast load
+        double pr, pi;
+        cprod<N, double>(wr, wi, pr, pi);
+        sr = fma(st.coef, pr, sr);
+        si = fma(st.coef, pi, si);
+        if (t + 1 < T) {
+            const double2* row = Vs + srow[st.slot * K1X_THREADS + tid];
+            // v_slot += dir  =>  (s - 2v)/2 decreases by dir
+            if (st.dir > 0) row_addsub<N, double, true>(wr, wi, row);
+            else row_addsub<N, double, false>(wr, wi, row);
+        }
+    }
+    const double scale = sqrt(fin_s * fout);
+    const double f = (double)tm.factor;
+    const double re = (f * sr) / scale, im = (f * si) / scale;
+    a.probs[k] = re * re + im * im;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+struct Plan {
+    int n = 0;
+    int n_types = 0;
+    std::vector<TypeMeta> meta;
+    uint64_t* d_keys = nullptr;
+    int* d_key_type = nullptr;
+    TypeMeta* d_meta = nullptr;
+    Step* d_prog = nullptr;
+    std::vector<int> order_by_T;  // type ids, heaviest first
+};
+
+struct K1xState {
+    std::map<int, Plan> plans;
+    unsigned int* d_counts = nullptr;
+    uint32_t* d_H = nullptr;
+    size_t H_cap = 0;
+    uint32_t* d_offsets = nullptr;
+    uint32_t* d_bucket = nullptr;
+    size_t bucket_cap = 0;
+    BlockWork* d_work = nullptr;
+    size_t work_cap = 0;
+};
+
+K1xState* k1x_create() { return new K1xState(); }
+
+void k1x_destroy(K1xState* st) {
+    if (!st) return;
+    for (auto& kv : st->plans) {
+        cudaFree(kv.second.d_keys);
+        cudaFree(kv.second.d_key_type);
+        cudaFree(kv.second.d_meta);
+        cudaFree(kv.second.d_prog);
+    }
+    cudaFree(st->d_counts);
+    cudaFree(st->d_H);
+    cudaFree(st->d_offsets);
+    cudaFree(st->d_bucket);
+    cudaFree(st->d_work);
+    delete st;
+}
+
+bool k1x_supported(int n) { return n >= 2 && n <= K1X_MAX_N; }
+
+static void partitions(int n, int maxpart, std::vector<int>& cur, std::vector<std::vector<int>>& out) {
+    if (n == 0) { out.push_back(cur); return; }
+    for (int p = std::min(n, maxpart); p >= 1; --p) {
+        cur.push_back(p);
+        partitions(n - p, p, cur, out);
+        cur.pop_back();
+    }
+}
+
+static double binom_d(int a, int b) {
+    double r = 1.0;
+    for (int i = 1; i <= b; ++i) r = r * (double)(a - b + i) / (double)i;
+    return std::floor(r + 0.5);
+}
+
+// reflected mixed-radix Gray walk (Knuth 7.2.1.1 Algorithm H) over the digits with radix > 1
+static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<Step>& prog) {
+    const int d = (int)s.size();
+    std::vector<int> R(d);
+    int h = -1;
+    for (int i = d - 1; i >= 0; --i)
+        if (s[i] % 2 == 1) { h = i; break; }
+    for (int i = 0; i < d; ++i) R[i] = s[i] + 1;
+    tm.factor = 1;
+    if (h >= 0) { R[h] = (s[h] + 1) / 2; tm.factor = 2; }
+    // fastest Gray digit = last slot: among equal multiplicities the slots are in ascending mode order and, in
+    // the reference's rank order, high modes change slowest from one state to the next, so the rows flipped most
+    // often are the ones neighbouring lanes share
+    std::vector<int> digits;
+    for (int i = d - 1; i >= 0; --i)
+        if (R[i] > 1) digits.push_back(i);
+    const int nd = (int)digits.size();
+    std::vector<int> a(nd, 0), o(nd, 1), f(nd + 1);
+    for (int j = 0; j <= nd; ++j) f[j] = j;
+    std::vector<int> v(d, 0);
+    tm.d = d;
+    tm.prog_off = (int)prog.size();
+    for (int i = 0; i < K1X_MAX_N; ++i) tm.s[i] = i < d ? s[i] : 0;
+    int T = 0;
+    for (;;) {
+        double coef = 1.0;
+        int sum = 0;
+        for (int i = 0; i < d; ++i) { coef *= binom_d(s[i], v[i]); sum += v[i]; }
+        Step st;
+        st.coef = (sum & 1) ? -coef : coef;
+        st.slot = 0;
+        st.dir = 0;
+        int j = f[0];
+        f[0] = 0;
+        if (j == nd) { prog.push_back(st); ++T; break; }
+        a[j] += o[j];
+        st.slot = digits[j];
+        st.dir = o[j];
+        v[digits[j]] += o[j];
+        if (a[j] == 0 || a[j] == R[digits[j]] - 1) { o[j] = -o[j]; f[j] = f[j + 1]; f[j + 1] = j + 1; }
+        prog.push_back(st);
+        ++T;
+    }
+    tm.T = T;
+}
+
+static int make_plan(K1xState* st, int n, Plan** out, std::string* err) {
+    auto it = st->plans.find(n);
+    if (it != st->plans.end()) { *out = &it->second; return 0; }
+    Plan pl;
+    pl.n = n;
+    std::vector<std::vector<int>> parts;
+    std::vector<int> cur;
+    partitions(n, n, cur, parts);
+    pl.n_types = (int)parts.size();
+    if (pl.n_types > K1X_MAX_TYPES) { *err = "too many multiplicity patterns"; return LWB_E_LIMIT; }
+    std::vector<Step> prog;
+    std::vector<std::pair<uint64_t, int>> keyed;
+    pl.meta.resize(pl.n_types);
+    for (int t = 0; t < pl.n_types; ++t) {
+        build_program(parts[t], pl.meta[t], prog);
+        int big[K1X_MAX_N];
+        int nb = 0;
+        for (int p : parts[t])
+            if (p >= 2) big[nb++] = p;
+        keyed.push_back({pack_key(big, nb), t});
+    }
+    std::sort(keyed.begin(), keyed.end());
+    std::vector<uint64_t> keys;
+    std::vector<int> key_type;
+    for (auto& kv : keyed) { keys.push_back(kv.first); key_type.push_back(kv.second); }
+    pl.order_by_T.resize(pl.n_types);
+    for (int t = 0; t < pl.n_types; ++t) pl.order_by_T[t] = t;
+    std::sort(pl.order_by_T.begin(), pl.order_by_T.end(), [&](int x, int y) { return pl.meta[x].T > pl.meta[y].T; });
+#define K1X_CU(call)                                                                  \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) { *err = std::string(#call ": ") + cudaGetErrorString(e_); return LWB_E_CUDA; } \
+    } while (0)
+    K1X_CU(cudaMalloc(&pl.d_keys, keys.size() * 8));
+    K1X_CU(cudaMalloc(&pl.d_key_type, key_type.size() * 4));
+    K1X_CU(cudaMalloc(&pl.d_meta, pl.meta.size() * sizeof(TypeMeta)));
+    K1X_CU(cudaMalloc(&pl.d_prog, prog.size() * sizeof(Step)));
+    K1X_CU(cudaMemcpy(pl.d_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
+    K1X_CU(cudaMemcpy(pl.d_key_type, key_type.data(), key_type.size() * 4, cudaMemcpyHostToDevice));
+    K1X_CU(cudaMemcpy(pl.d_meta, pl.meta.data(), pl.meta.size() * sizeof(TypeMeta), cudaMemcpyHostToDevice));
+    K1X_CU(cudaMemcpy(pl.d_prog, prog.data(), prog.size() * sizeof(Step), cudaMemcpyHostToDevice));
+    st->plans[n] = pl;
+    *out = &st->plans[n];
+    return 0;
+}
+
+typedef void (*K1xFn)(K1xArgs);
+template <int N>
+struct K1xTable {
+    static void fill(K1xFn* t) { t[N] = k1x_kernel<N>; K1xTable<N - 1>::fill(t); }
+};
+template <>
+struct K1xTable<1> {
+    static void fill(K1xFn*) {}
+};
+
+int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, const double2* d_U, int m,
+                    const uint8_t* d_in_state, int n, uint64_t r0, uint64_t cnt, double* d_probs, uint64_t* launches,
+                    std::string* err) {
+    static K1xFn table[K1X_MAX_N + 1];
+    static bool table_init = false;
+    if (!table_init) { K1xTable<K1X_MAX_N>::fill(table); table_init = true; }
+    if (!k1x_supported(n) || cnt >= (1ull << 32)) { *err = "k1x: unsupported size"; return LWB_E_LIMIT; }
+    if (cnt == 0) return 0;
+    Plan* pl = nullptr;
+    int rc = make_plan(st, n, &pl, err);
+    if (rc) return rc;
+    if (!st->d_counts) {
+        K1X_CU(cudaMalloc(&st->d_counts, K1X_MAX_TYPES * 4));
+        K1X_CU(cudaMalloc(&st->d_offsets, K1X_MAX_TYPES * 4));
+    }
+    if (st->bucket_cap < cnt) {
+        if (st->d_bucket) K1X_CU(cudaFree(st->d_bucket));
+        st->d_bucket = nullptr;
+        K1X_CU(cudaMalloc(&st->d_bucket, cnt * 4));
+        st->bucket_cap = cnt;
+    }
+    // pass 1: per-block counts, then per-type exclusive scan over the blocks (device) and totals (host)
+    const uint32_t nb = (uint32_t)((cnt + K1X_CL_THREADS - 1) / K1X_CL_THREADS);
+    const size_t h_entries = (size_t)pl->n_types * nb;
+    if (st->H_cap < h_entries) {
+        if (st->d_H) K1X_CU(cudaFree(st->d_H));
+        st->d_H = nullptr;
+        K1X_CU(cudaMalloc(&st->d_H, h_entries * 4));
+        st->H_cap = h_entries;
+    }
+    ClassifyArgs ca;
+    ca.bin = d_bin; ca.m = m; ca.n = n; ca.r0 = r0; ca.cnt = cnt; ca.keys = pl->d_keys; ca.key_type = pl->d_key_type;
+    ca.n_types = pl->n_types; ca.nb = nb; ca.H = st->d_H; ca.offsets = st->d_offsets; ca.bucket = st->d_bucket; ca.fill = 0;
+    k1x_classify_kernel<K1X_MAX_N><<<nb, K1X_CL_THREADS, 0, stream>>>(ca);
+    k1x_scan_kernel<<<pl->n_types, 1024, 0, stream>>>(st->d_H, nb, st->d_counts);
+    *launches += 2;
+    std::vector<unsigned int> counts(pl->n_types);
+    K1X_CU(cudaMemcpyAsync(counts.data(), st->d_counts, pl->n_types * 4, cudaMemcpyDeviceToHost, stream));
+    K1X_CU(cudaStreamSynchronize(stream));
+    // bucket layout (heaviest types first) and the block work list
+    std::vector<uint32_t> offsets(pl->n_types, 0);
+    std::vector<BlockWork> work;
+    uint32_t off = 0;
+    for (int t : pl->order_by_T) {
+        offsets[t] = off;
+        for (uint32_t b = 0; b < counts[t]; b += K1X_THREADS) {
+            BlockWork w;
+            w.type = t;
+            w.begin = off + b;
+            w.end = off + std::min<uint32_t>(counts[t], b + K1X_THREADS);
+            work.push_back(w);
+        }
+        off += counts[t];
+    }
+    if (st->work_cap < work.size()) {
+        if (st->d_work) K1X_CU(cudaFree(st->d_work));
+        st->d_work = nullptr;
+        K1X_CU(cudaMalloc(&st->d_work, work.size() * sizeof(BlockWork)));
+        st->work_cap = work.size();
+    }
+    K1X_CU(cudaMemcpyAsync(st->d_offsets, offsets.data(), pl->n_types * 4, cudaMemcpyHostToDevice, stream));
+    K1X_CU(cudaMemcpyAsync(st->d_work, work.data(), work.size() * sizeof(BlockWork), cudaMemcpyHostToDevice, stream));
+    // pass 2: stable fill of the buckets
+    ca.fill = 1;
+    k1x_classify_kernel<K1X_MAX_N><<<nb, K1X_CL_THREADS, 0, stream>>>(ca);
+    ++*launches;
+    // main kernel: one block per 256 permanents of one type
+    K1xArgs ka;
+    ka.bin = d_bin; ka.U = d_U; ka.m = m; ka.in_state = d_in_state; ka.r0 = r0; ka.meta = pl->d_meta; ka.prog = pl->d_prog;
+    ka.work = st->d_work; ka.bucket = st->d_bucket; ka.probs = d_probs;
+    const size_t smem = (size_t)m * (n | 1) * 16 + (size_t)n * K1X_THREADS * 4;
+    K1xFn fn = table[n];
+    if (smem > 48 * 1024) K1X_CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fn<<<(unsigned)work.size(), K1X_THREADS, smem, stream>>>(ka);
+    ++*launches;
+    K1X_CU(cudaGetLastError());
+    // (the host vectors above are pageable: cudaMemcpyAsync has staged them before returning)
+    return 0;
+}
+
+}  // namespace lwb

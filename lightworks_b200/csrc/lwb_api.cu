@@ -12,6 +12,7 @@
 
 #include "../../include/lwb200.h"
 #include "fock.cuh"
+#include "k1x.h"
 #include "misc_kernels.cuh"
 #include "perm_kernels.cuh"
 #include "slos_kernels.cuh"
@@ -56,6 +57,7 @@ struct lwb_context {
     uint64_t* d_bin = nullptr;
     Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall;
     uint64_t launches = 0;
+    K1xState* k1x = nullptr;
     std::mutex mu;
 };
 
@@ -84,6 +86,7 @@ static int ensure(lwb_handle h, Buf& b, size_t bytes) {
 static std::vector<K1Variant> g_k1;
 static const K2Variant* g_k2[LWB_K2_MAX_N + 1];
 static int g_tune_logl[LWB_K1_MAX_N + 1];
+static int g_multiplicity_aware = 1;  // lwb_set_option("multiplicity_aware", 0/1)
 static std::once_flag g_tables_once;
 
 static void load_tables() {
@@ -149,6 +152,7 @@ int lwb_create(int device, lwb_handle* out) {
     CU(cudaMalloc(&h->d_bin, sizeof g_bin));
     CU(cudaMemcpy(h->d_bin, host_bin(), sizeof g_bin, cudaMemcpyHostToDevice));
     load_tables();
+    h->k1x = k1x_create();
     *out = h;
     return 0;
 }
@@ -160,6 +164,7 @@ int lwb_destroy(lwb_handle h) {
     for (Buf* b : {&h->bU, &h->bIn, &h->bOut, &h->bRes, &h->bPart, &h->bTmp, &h->bLayerA, &h->bLayerB, &h->bProbs,
                    &h->bMarg, &h->bFirst, &h->bSmall})
         if (b->p) cudaFree(b->p);
+    k1x_destroy(h->k1x);
     if (h->d_bin) cudaFree(h->d_bin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -204,6 +209,12 @@ int lwb_set_tuning(int n, int log_l, int minb) {
     }
     g_tune_logl[n] = log_l;
     return 0;
+}
+
+int lwb_set_option(const char* name, int value) {
+    if (!name) return fail(LWB_E_ARG, "null option name");
+    if (!strcmp(name, "multiplicity_aware")) { g_multiplicity_aware = value ? 1 : 0; return 0; }
+    return fail(LWB_E_ARG, "unknown option %s", name);
 }
 
 int lwb_launch_count(lwb_handle h, uint64_t* count) {
@@ -344,6 +355,15 @@ static int launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* 
     if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
     if (n_in < 1 || n_in > 65535) return fail(LWB_E_ARG, "n_in=%d outside [1,65535]", n_in);
     if (n_out == 0) return 0;
+    if (g_multiplicity_aware && !d_outs && n_in == 1 && want_probs && dtype == LWB_C128 && k1x_supported(n) &&
+        n >= 7 && n_out < (1ull << 32)) {  // by n only: a rank-range shard is bit-identical to the same slice of the whole
+        // full-basis rank range: bunched output states repeat rows, walk prod(s_i+1)/2 terms instead of 2^(n-1)
+        std::string err;
+        int rc = k1x_basis_probs(h->k1x, h->stream, h->d_bin, (const double2*)d_U, m, d_ins, n, r0, n_out, d_out,
+                                 &h->launches, &err);
+        if (rc) return fail(rc, "%s", err.c_str());
+        return 0;
+    }
     const K1Variant* v = pick_k1(n);
     const int gpb = K1_THREADS >> v->log_l;
     const size_t smem = (size_t)m * n * (dtype == LWB_C128 ? 16 : 8) + (size_t)gpb * n * sizeof(int);

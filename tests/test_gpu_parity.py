@@ -290,3 +290,25 @@ def test_error_behaviour(lb, ctx):
     for cls in (lb.PermanentBackend, lb.SLOSBackend):
         d = cls().full_probability_distribution(circ, lb.State([0, 0, 0, 0]))
         assert d == {lb.State([0, 0, 0, 0]): 1.0}
+
+
+# ---------------------------------------------------------------- multiplicity-aware walk (K1x) vs expanded rows (K1)
+@pytest.mark.parametrize("m,n,seed", [(9, 7, 4), (16, 8, 5), (6, 9, 6), (14, 10, 7), (5, 12, 8), (4, 16, 9), (20, 7, 10)])
+def test_multiplicity_aware_equals_expanded(ctx, lb, m, n, seed):
+    """Full-basis probabilities through the multiplicity-aware Glynn walk (default for ranges >= 4096 states)
+    equal the expanded-row kernel and the oracle; bunched INPUTS (repeated columns) included."""
+    U = O.random_unitary(m, seed)  # noqa: N806
+    rng = np.random.default_rng(seed)
+    ins = np.bincount(rng.integers(0, m, n), minlength=m).astype(np.uint8)
+    S = lb.fock_count(m, n)  # noqa: N806
+    r0, cnt = (S // 7, min(S - S // 7, 200000))
+    lb.set_option("multiplicity_aware", 1)
+    fast = ctx.perm_basis_probs(U, ins, r0, cnt)
+    lb.set_option("multiplicity_aware", 0)
+    try:
+        plain = ctx.perm_basis_probs(U, ins, r0, cnt)
+    finally:
+        lb.set_option("multiplicity_aware", 1)
+    assert rel_close(fast, plain, 1e-10, 1e-18)
+    ref = O.basis_probabilities(U, ins, r0, min(cnt, 500), threads=8)
+    assert rel_close(fast[: len(ref)], ref, REL128, 1e-18)
