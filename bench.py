@@ -37,6 +37,38 @@ METRIC = "output-state probabilities/sec (complex128 10x10 permanents, full dist
 UNIT = "probabilities/s"
 
 
+def average_terms(m: int, n: int) -> float:
+    """Average number of terms of the multiplicity-aware walk over ALL outputs of n photons in m modes:
+    prod(s_i + 1) / (2 if some s_i is odd else 1) per multiplicity pattern, weighted by its number of states."""
+    from math import comb, factorial
+
+    def parts(k, mx):
+        if k == 0:
+            yield []
+            return
+        for p in range(min(k, mx), 0, -1):
+            for rest in parts(k - p, p):
+                yield [p, *rest]
+
+    tot = work = 0
+    for part in parts(n, n):
+        d = len(part)
+        if d > m:
+            continue
+        cnt = factorial(m) // factorial(m - d)
+        for v in {x: part.count(x) for x in part}.values():
+            cnt //= factorial(v)
+        t = 1
+        for s_ in part:
+            t *= s_ + 1
+        if any(s_ % 2 for s_ in part):
+            t //= 2
+        tot += cnt
+        work += cnt * t
+    assert tot == comb(m + n - 1, n)
+    return work / tot
+
+
 def flops_per_perm(n: int) -> float:
     """Algorithmic FP64 flops of one n x n complex128 Glynn/Gray permanent."""
     return 2.0 ** (n - 1) * (8 * n - 4)
@@ -300,19 +332,36 @@ def main() -> int:  # noqa: PLR0915
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = S * args.steps / e2e_s
 
-    # ---- roofline of the dominant kernel (K1 perm_states_kernel<10,...>) ----
+    # ---- roofline of the dominant kernel ----
+    # The default path walks the multiplicity-aware Glynn sum (K1x: prod(s_i+1)/2 terms for an output with
+    # occupations s_i); the plain expanded-row kernel (K1: 2^(n-1) terms for every output) is timed beside it.
+    # `achieved` is ALGORITHMIC flops (2^(n-1)(8n-4) per permanent) over the kernel time for both;
+    # `executed_frac` counts the FP64 work K1x really issues (terms x (8n-2)).
     peak = ctx.fp64_peak()  # measured live: MEASURED_PEAKS.json carries no FP64 entry
-    with torch.cuda.stream(stream):
-        kev = []
-        for _ in range(3):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+
+    def kernel_ms(reps=3):
+        with torch.cuda.stream(stream):
+            kev = []
+            for _ in range(reps):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
+                e1.record(stream)
+                kev.append((e0, e1))
+            stream.synchronize()
+        return statistics.mean(a.elapsed_time(b) for a, b in kev)
+
+    k_ms = kernel_ms()
+    lb.set_option("multiplicity_aware", 0)
+    try:
+        with torch.cuda.stream(stream):
             ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
-            e1.record(stream)
-            kev.append((e0, e1))
-        stream.synchronize()
-    k_ms = statistics.mean(a.elapsed_time(b) for a, b in kev)
-    achieved = cnt * flops_per_perm(N_PH) / (k_ms * 1e-3)
+        plain_ms = kernel_ms()
+    finally:
+        lb.set_option("multiplicity_aware", 1)
+    alg = cnt * flops_per_perm(N_PH)
+    avg_terms = average_terms(M, N_PH)
+    executed = cnt * avg_terms * (8 * N_PH - 2)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath):
@@ -320,14 +369,22 @@ def main() -> int:  # noqa: PLR0915
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "fp64", "kernel": "perm_states_kernel<N=10> (batched Glynn/Gray-code permanents)",
-                "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel_ms": k_ms,
-                "flops_per_unit": flops_per_perm(N_PH), "units_per_launch": cnt,
-                "peak_source": "lwb_fp64_peak DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no "
-                               "FP64 entry; nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)",
-                "note": "tensor cores unused: not a dense contraction; ceiling of the 6n-2 instruction Glynn step "
-                        "is (8n-4)/(12n-4) = 0.655 of DFMA peak at n=10"}
+    peak_src = ("lwb_fp64_peak DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 entry; nominal "
+                "148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)")
+    roofline = {"bound": "fp64", "kernel": "k1x_kernel<N=10> + bucketing passes (multiplicity-aware Glynn/Gray walk)",
+                "achieved": alg / (k_ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+                "frac": alg / (k_ms * 1e-3) / peak, "executed_frac": executed / (k_ms * 1e-3) / peak,
+                "average_terms_per_permanent": avg_terms, "terms_expanded": 2 ** (N_PH - 1),
+                "traffic": traffic, "kernel_ms": k_ms, "flops_per_unit": flops_per_perm(N_PH), "units_per_launch": cnt,
+                "peak_source": peak_src,
+                "note": "frac uses the reference algorithm's flop count per permanent, so a walk that skips the repeated-row "
+                        "terms of bunched outputs can exceed the 0.57 register-file ceiling of the expanded-row kernel; "
+                        "tensor cores unused (not a dense contraction)"}
+    roofline_plain = {"bound": "fp64", "kernel": "perm_states_kernel<N=10> (expanded rows, 2^(n-1) Gray terms per output)",
+                      "achieved": alg / (plain_ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+                      "frac": alg / (plain_ms * 1e-3) / peak, "kernel_ms": plain_ms,
+                      "note": "ceilings: (8n-4)/(12n-4) = 0.655 if every FP64 instruction issued in 2 cycles; 0.57 measured "
+                              "limit because a DFMA with three distinct register operands issues in 3 (lwb_fp64_probe)"}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -337,7 +394,7 @@ def main() -> int:  # noqa: PLR0915
                    "parallelism": f"fock-rank-range shards x{world}" + (" + NCCL all-gather/all-reduce" if world > 1 else ""),
                    "l2": "256 MiB flush between timed steps (outside the event pairs); outputs 740 MB > 126 MB L2",
                    "check_sum_of_probabilities": total_sum},
-        "roofline": roofline,
+        "roofline": roofline, "roofline_expanded_rows": roofline_plain,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(U.nbytes + ins.nbytes),
                 "d2h_bytes_per_step": int(cnt * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
                 "api": "lwb_perm_basis_probs (host buffers, pinned) via lightworks_b200.Context.perm_basis_probs"},

@@ -13,6 +13,13 @@
 
 namespace lwb {
 
+#ifndef K1X_UNROLL
+#define K1X_UNROLL 2
+#endif
+#ifndef K1X_EARLY_LOADS
+#define K1X_EARLY_LOADS 1
+#endif
+constexpr int k1x_unroll = K1X_UNROLL;
 constexpr int K1X_THREADS = 256;
 constexpr int K1X_MAX_N = 16;       // kernels instantiated for 2 <= n <= 16
 constexpr int K1X_CL_THREADS = 1024;  // one state per thread in the bucketing passes
@@ -79,6 +86,7 @@ struct ClassifyArgs {
     uint32_t* H;               // [n_types][nb]: pass 1 writes per-block counts; scanned in place to exclusive prefixes
     const uint32_t* offsets;   // pass 2: first bucket slot of every type
     uint32_t* bucket;          // pass 2 output
+    unsigned char* types;      // [cnt] type of every state: written by pass 1, read by pass 2
     int fill;
 };
 
@@ -99,9 +107,14 @@ __global__ void __launch_bounds__(K1X_CL_THREADS) k1x_classify_kernel(ClassifyAr
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int t = K1X_MAX_TYPES + lane;  // invalid lanes never match anybody
     if (valid) {
-        int x[NMAX];
-        colex_unrank(a.bin, a.r0 + k, a.n, a.m, x);
-        t = a.key_type[find_type(a.keys, a.n_types, key_of_modes<NMAX>(x, a.n))];
+        if (a.fill) {
+            t = a.types[k];
+        } else {
+            int x[NMAX];
+            colex_unrank(a.bin, a.r0 + k, a.n, a.m, x);
+            t = a.key_type[find_type(a.keys, a.n_types, key_of_modes<NMAX>(x, a.n))];
+            a.types[k] = (unsigned char)t;
+        }
     }
     const unsigned peers = __match_any_sync(0xffffffffu, t);
     const int in_warp = __popc(peers & ((1u << lane) - 1u));
@@ -230,19 +243,42 @@ __global__ void __launch_bounds__(K1X_THREADS) k1x_kernel(K1xArgs a) {
     const Step* prog = a.prog + tm.prog_off;
     const int T = tm.T;
     double sr = 0.0, si = 0.0;
-#pragma unroll 1
+    // The step descriptor and this lane's row address are fetched one term ahead, and the row of a flip is
+    // loaded BEFORE the product chain of the same term, so the shared-memory latency hides behind ~40 FP64
+    // instructions instead of stalling the adds.
+    const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+    Step st = prog[0];  // same address for every lane of the block: one broadcast load
+    uint32_t rowaddr = vs_base + 16u * (uint32_t)srow[st.slot * K1X_THREADS + tid];
+#pragma unroll k1x_unroll
     for (int t = 0; t < T; ++t) {
-        const Step st = prog[t];  // same address for every lane of the block: one broadcast load
+        const Step nx = prog[t + 1 < T ? t + 1 : t];
+        const uint32_t nrowaddr = vs_base + 16u * (uint32_t)srow[nx.slot * K1X_THREADS + tid];
+#if K1X_EARLY_LOADS
+        double2 rv[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rv[j].x), "=d"(rv[j].y) : "r"(rowaddr + 16u * j));
+#endif
         double pr, pi;
         cprod<N, double>(wr, wi, pr, pi);
         sr = fma(st.coef, pr, sr);
         si = fma(st.coef, pi, si);
-        if (t + 1 < T) {
-            const double2* row = Vs + srow[st.slot * K1X_THREADS + tid];
-            // v_slot += dir  =>  (s - 2v)/2 decreases by dir
-            if (st.dir > 0) row_addsub<N, double, true>(wr, wi, row);
-            else row_addsub<N, double, false>(wr, wi, row);
+        // v_slot += dir  =>  (s - 2v)/2 decreases by dir   (the update after the last term is harmless)
+        const double sg = st.dir > 0 ? -1.0 : 1.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+#if K1X_EARLY_LOADS
+            const double2 v = rv[j];
+#else
+            double2 v;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(rowaddr + 16u * j));
+#endif
+            if (st.dir > 0) { wr[j] -= v.x; wi[j] -= v.y; }
+            else { wr[j] += v.x; wi[j] += v.y; }
         }
+        (void)sg;
+        st = nx;
+        rowaddr = nrowaddr;
     }
     const double scale = sqrt(fin_s * fout);
     const double f = (double)tm.factor;
@@ -267,6 +303,7 @@ struct K1xState {
     unsigned int* d_counts = nullptr;
     uint32_t* d_H = nullptr;
     size_t H_cap = 0;
+    unsigned char* d_types = nullptr;
     uint32_t* d_offsets = nullptr;
     uint32_t* d_bucket = nullptr;
     size_t bucket_cap = 0;
@@ -286,6 +323,7 @@ void k1x_destroy(K1xState* st) {
     }
     cudaFree(st->d_counts);
     cudaFree(st->d_H);
+    cudaFree(st->d_types);
     cudaFree(st->d_offsets);
     cudaFree(st->d_bucket);
     cudaFree(st->d_work);
@@ -430,6 +468,9 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
         if (st->d_bucket) K1X_CU(cudaFree(st->d_bucket));
         st->d_bucket = nullptr;
         K1X_CU(cudaMalloc(&st->d_bucket, cnt * 4));
+        if (st->d_types) K1X_CU(cudaFree(st->d_types));
+        st->d_types = nullptr;
+        K1X_CU(cudaMalloc(&st->d_types, cnt));
         st->bucket_cap = cnt;
     }
     // pass 1: per-block counts, then per-type exclusive scan over the blocks (device) and totals (host)
@@ -443,7 +484,7 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
     }
     ClassifyArgs ca;
     ca.bin = d_bin; ca.m = m; ca.n = n; ca.r0 = r0; ca.cnt = cnt; ca.keys = pl->d_keys; ca.key_type = pl->d_key_type;
-    ca.n_types = pl->n_types; ca.nb = nb; ca.H = st->d_H; ca.offsets = st->d_offsets; ca.bucket = st->d_bucket; ca.fill = 0;
+    ca.n_types = pl->n_types; ca.nb = nb; ca.H = st->d_H; ca.offsets = st->d_offsets; ca.bucket = st->d_bucket; ca.types = st->d_types; ca.fill = 0;
     k1x_classify_kernel<K1X_MAX_N><<<nb, K1X_CL_THREADS, 0, stream>>>(ca);
     k1x_scan_kernel<<<pl->n_types, 1024, 0, stream>>>(st->d_H, nb, st->d_counts);
     *launches += 2;
