@@ -91,7 +91,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(self.gpu)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -101,9 +101,9 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float | None = None, t1: float | None = None) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -113,7 +113,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        window = [r for (ts, r) in self.rows if t0 is None or (t0 <= ts <= t1 + 0.05)]
+        scope = "timed region"
+        if not window:  # region shorter than the sampling period: use every sample taken under load (warm-up + region)
+            window = [r for (_, r) in self.rows[1:]] or [r for (_, r) in self.rows]
+            scope = "warm-up + timed region (region shorter than the sampling period)"
+        for r in window:
             if len(r) < 9:
                 continue
             try:
@@ -128,7 +133,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -148,6 +153,7 @@ def cpu_port_baseline(U, ins, sample: int, threads: int) -> dict:  # noqa: N803
 
 def run_reference_arm(args) -> int:
     """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    protect_stdout()
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -199,12 +205,32 @@ def run_reference_arm(args) -> int:
                  "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
                  "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                  "gpu_launches": 0})
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The driver parses ONE JSON line from stdout; NCCL ("NCCL version ...") and other libraries print there
+    too.  Route fd 1 to stderr for the whole run and keep the real stdout for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main() -> int:  # noqa: PLR0915
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -242,7 +268,9 @@ def main() -> int:  # noqa: PLR0915
     U = O.random_unitary(M, SEED)  # noqa: N806  == lw.random_unitary(24, seed=3) (sdk/utils/random.py:66-67)
     ins = np.array([1] * N_PH + [0] * (M - N_PH), dtype=np.uint8)
     S = lb.fock_count(M, N_PH)  # noqa: N806
-    r0, r1 = sharding.rank_range(S, rank, world)
+    # contiguous rank-range shards; boundaries equalise the WORK of the multiplicity-aware walk (early ranks bunch more)
+    shard_ranges = sharding.work_balanced_ranges(M, N_PH, world)
+    r0, r1 = shard_ranges[rank]
     cnt = r1 - r0
 
     def barrier():
@@ -250,23 +278,24 @@ def main() -> int:  # noqa: PLR0915
             dist.barrier()
         torch.cuda.synchronize()
 
+    gather_sizes = [b - a for a, b in shard_ranges]
+    max_cnt = max(gather_sizes)
     with torch.cuda.stream(stream):
         d_U = torch.from_numpy(U).cuda()  # noqa: N806  resident inputs for the device-timed region
         d_ins = torch.from_numpy(ins).cuda()
-        d_probs = torch.empty(cnt, dtype=torch.float64, device="cuda")
-        d_full = torch.empty(S, dtype=torch.float64, device="cuda") if world > 1 else None
+        # shards have unequal lengths (equal work): every rank writes its shard at the head of a max_cnt slot and
+        # ONE ncclAllGather moves the slots; the distribution on every rank is the ragged view
+        # d_full.view(world, max_cnt)[r, :gather_sizes[r]] (padding stays zero)
+        d_slot = torch.zeros(max_cnt, dtype=torch.float64, device="cuda")
+        d_probs = d_slot[:cnt]
+        d_full = torch.zeros(world * max_cnt, dtype=torch.float64, device="cuda") if world > 1 else None
         d_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    gather_sizes = [sharding.rank_range(S, r, world)[1] - sharding.rank_range(S, r, world)[0] for r in range(world)]
 
     def device_step():
         ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
         if world > 1:
-            outs = list(torch.split(d_full, gather_sizes))
-            if len(set(gather_sizes)) == 1:
-                dist.all_gather_into_tensor(d_full, d_probs)
-            else:
-                dist.all_gather(outs, d_probs)
+            dist.all_gather_into_tensor(d_full, d_slot)
             torch.sum(d_probs, dim=0, keepdim=True, out=d_sum)
             dist.all_reduce(d_sum)
 
@@ -286,8 +315,7 @@ def main() -> int:  # noqa: PLR0915
         between steps is not inside any event pair.  Returns (sum of event ms, wall ms)."""
         evs = []
         barrier()
-        if sampler:
-            sampler.start()
+        t_start = time.time()
         w0 = time.perf_counter()
         with torch.cuda.stream(stream):
             for _ in range(k):
@@ -299,7 +327,7 @@ def main() -> int:  # noqa: PLR0915
                 evs.append((e0, e1))
         barrier()
         wall = (time.perf_counter() - w0) * 1e3
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stop(t_start, time.time()) if sampler else None
         ms = sum(a.elapsed_time(b) for a, b in evs)
         return ms, wall, clocks
 
@@ -311,11 +339,13 @@ def main() -> int:  # noqa: PLR0915
         return float(t)
 
     # ---- warm-up, then the device-resident timed region ----
+    sampler = ClockSampler(local)
+    sampler.start()  # started before the warm-up so that samples exist even when the timed region is tens of ms
     with torch.cuda.stream(stream):
         for _ in range(warmup):
             device_step()
     l0 = ctx.launch_count()
-    dev_ms, dev_wall, clocks = timed(device_step, args.steps, ClockSampler(local))
+    dev_ms, dev_wall, clocks = timed(device_step, args.steps, sampler)
     launches = ctx.launch_count() - l0
     dev_ms = max_over_ranks(dev_ms)
     total_sum = float(d_probs.sum()) if world == 1 else float(d_sum)
@@ -426,7 +456,7 @@ def main() -> int:  # noqa: PLR0915
         if not args.no_extras:
             line["extra"] = extras(ctx, stream, peak, d_U, torch, np, O, _lib)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

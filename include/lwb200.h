@@ -58,6 +58,11 @@ int lwb_set_tuning(int n, int log_l, int minb);
  * multiplicity-aware Glynn walk (prod(s_i+1)/2 terms for an output with occupations s_i) instead of
  * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel. */
 int lwb_set_option(const char* name, int value);
+/* Host-only view of the multiplicity-aware walk for n photons (2 <= n <= 16): pattern = index of a partition of
+ * n (descending lexicographic order); returns its multiplicities (n_distinct entries, descending), the number of
+ * terms of the walk, the symmetry factor (2 if halved) and the sum of |coefficients| (= 2^n / factor). */
+int lwb_multiplicity_plan(int n, int pattern, int* n_patterns, int* multiplicities, int* n_distinct, int* n_terms,
+                          int* symmetry_factor, double* abs_coef_sum);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int lwb_launch_count(lwb_handle h, uint64_t* count);
 

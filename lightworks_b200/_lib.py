@@ -44,6 +44,7 @@ SIGNATURES = {
     "lwb_device_info": (_i, [_vp, _pi, _pi, C.c_char_p, _i]),
     "lwb_set_tuning": (_i, [_i, _i, _i]),
     "lwb_set_option": (_i, [C.c_char_p, _i]),
+    "lwb_multiplicity_plan": (_i, [_i, _i, _pi, _pi, _pi, _pi, _pi, _pdbl]),
     "lwb_launch_count": (_i, [_vp, _pu64]),
     "lwb_fock_count": (_i, [_i, _i, _pu64]),
     "lwb_fock_rank": (_i, [_i, _vp, _pu64]),
@@ -361,6 +362,21 @@ _dev_methods()
 
 def set_option(name: str, value: int):
     check(cdll().lwb_set_option(name.encode(), int(value)))
+
+
+def multiplicity_plan(n: int) -> list[dict]:
+    """Host-only: the walk of the multiplicity-aware permanent for every multiplicity pattern of n photons."""
+    out = []
+    npat = C.c_int(0)
+    t = 0
+    while True:
+        s_ = (C.c_int * 64)()
+        d, T, f, a = C.c_int(0), C.c_int(0), C.c_int(0), C.c_double(0)  # noqa: N806
+        check(cdll().lwb_multiplicity_plan(n, t, C.byref(npat), s_, C.byref(d), C.byref(T), C.byref(f), C.byref(a)))
+        out.append({"s": list(s_[: d.value]), "terms": T.value, "factor": f.value, "abs_coef_sum": a.value})
+        t += 1
+        if t >= npat.value:
+            return out
 
 
 def set_tuning(n: int, log_l: int = -1, minb: int = -1):

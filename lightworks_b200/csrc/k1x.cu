@@ -2,6 +2,7 @@
 #include "k1x.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -331,6 +332,32 @@ void k1x_destroy(K1xState* st) {
 }
 
 bool k1x_supported(int n) { return n >= 2 && n <= K1X_MAX_N; }
+
+static void partitions(int n, int maxpart, std::vector<int>& cur, std::vector<std::vector<int>>& out);
+static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<Step>& prog);
+
+// Host-only description of the walk programs for n photons (no device needed): number of multiplicity patterns,
+// and for pattern index t (partitions of n in descending lexicographic order) its multiplicities, term count,
+// symmetry factor and the sum of its coefficients' absolute values (= 2^n / factor... a checksum of the walk).
+int k1x_plan_info(int n, int t, int* n_types, int* s_out, int* d_out, int* T_out, int* factor_out, double* abs_coef_sum) {
+    if (!k1x_supported(n)) return LWB_E_LIMIT;
+    std::vector<std::vector<int>> parts;
+    std::vector<int> cur;
+    partitions(n, n, cur, parts);
+    *n_types = (int)parts.size();
+    if (t < 0 || t >= (int)parts.size()) return LWB_E_ARG;
+    TypeMeta tm;
+    std::vector<Step> prog;
+    build_program(parts[t], tm, prog);
+    for (int i = 0; i < tm.d; ++i) s_out[i] = tm.s[i];
+    *d_out = tm.d;
+    *T_out = tm.T;
+    *factor_out = tm.factor;
+    double a = 0.0;
+    for (const Step& st : prog) a += std::fabs(st.coef);
+    *abs_coef_sum = a;
+    return 0;
+}
 
 static void partitions(int n, int maxpart, std::vector<int>& cur, std::vector<std::vector<int>>& out) {
     if (n == 0) { out.push_back(cur); return; }

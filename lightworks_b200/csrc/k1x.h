@@ -24,6 +24,7 @@ struct K1xState;  // cached plans + scratch buffers (owned by the context)
 K1xState* k1x_create();
 void k1x_destroy(K1xState* st);
 bool k1x_supported(int n);
+int k1x_plan_info(int n, int t, int* n_types, int* s_out, int* d_out, int* T_out, int* factor_out, double* abs_coef_sum);
 
 // probs[k] = |<basis[r0+k]|U|in>|^2 for k in [0, cnt), all pointers on the device; enqueues on `stream`
 // (one small device->host copy of the per-type counts synchronises the stream once).

@@ -217,6 +217,15 @@ int lwb_set_option(const char* name, int value) {
     return fail(LWB_E_ARG, "unknown option %s", name);
 }
 
+int lwb_multiplicity_plan(int n, int pattern, int* n_patterns, int* multiplicities, int* n_distinct, int* n_terms,
+                          int* symmetry_factor, double* abs_coef_sum) {
+    if (!n_patterns || !multiplicities || !n_distinct || !n_terms || !symmetry_factor || !abs_coef_sum)
+        return fail(LWB_E_ARG, "null argument");
+    int rc = k1x_plan_info(n, pattern, n_patterns, multiplicities, n_distinct, n_terms, symmetry_factor, abs_coef_sum);
+    if (rc) return fail(rc, "no multiplicity-aware plan for n=%d pattern=%d", n, pattern);
+    return 0;
+}
+
 int lwb_launch_count(lwb_handle h, uint64_t* count) {
     if (!h || !count) return fail(LWB_E_ARG, "null");
     *count = h->launches;

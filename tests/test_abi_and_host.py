@@ -104,3 +104,31 @@ def test_state_mirror_matches_reference_semantics():
     c = lb.CompiledCircuitView(np.eye(5), n_modes=3)
     assert c.loss_modes == 2
     assert O.fock_count(5, 2) == lb.fock_count(5, 2)
+
+
+def test_multiplicity_plan_host():
+    """The pre-computed walks of the multiplicity-aware permanent (csrc/k1x.cu), checked without a GPU:
+    every partition of n appears once, terms = prod(s_i + 1) / factor, and the binomial coefficients of a walk
+    sum to 2^n / factor (each tuple v carries prod C(s_i, v_i) sign vectors of the expanded-row Glynn sum)."""
+    from math import prod
+
+    def n_partitions(n):
+        p = [1] + [0] * n
+        for k in range(1, n + 1):
+            for i in range(k, n + 1):
+                p[i] += p[i - k]
+        return p[n]
+
+    for n in (2, 5, 10, 13):
+        plan = _lib.multiplicity_plan(n)
+        assert len(plan) == n_partitions(n)
+        assert len({tuple(p["s"]) for p in plan}) == len(plan)
+        for p in plan:
+            s = p["s"]
+            assert sum(s) == n and s == sorted(s, reverse=True)
+            odd = any(x % 2 for x in s)
+            assert p["factor"] == (2 if odd else 1)
+            assert p["terms"] == prod(x + 1 for x in s) // p["factor"]
+            assert p["abs_coef_sum"] == 2**n / p["factor"]
+    with pytest.raises(ValueError):
+        _lib.multiplicity_plan(17)
