@@ -278,26 +278,41 @@ def main() -> int:  # noqa: PLR0915
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_sizes = [b - a for a, b in shard_ranges]
-    max_cnt = max(gather_sizes)
+    # Every shard is cut into SUB pieces; the all-gather of piece j (NCCL, side stream) overlaps the kernel of
+    # piece j+1.  Pieces have unequal lengths across ranks (equal work), so every rank writes its piece at the head of
+    # a max-length slot and ONE ncclAllGather per piece moves the slots; the distribution on every rank is the ragged
+    # view  d_full[j].view(world, slot_j)[r, :len(piece j of rank r)]  (padding stays zero).
+    SUB = 4 if world > 1 else 1  # noqa: N806
+    pieces = [[(a + (b - a) * j // SUB, a + (b - a) * (j + 1) // SUB) for j in range(SUB)] for a, b in shard_ranges]
+    slot_len = [max(pieces[r][j][1] - pieces[r][j][0] for r in range(world)) for j in range(SUB)]
     with torch.cuda.stream(stream):
         d_U = torch.from_numpy(U).cuda()  # noqa: N806  resident inputs for the device-timed region
         d_ins = torch.from_numpy(ins).cuda()
-        # shards have unequal lengths (equal work): every rank writes its shard at the head of a max_cnt slot and
-        # ONE ncclAllGather moves the slots; the distribution on every rank is the ragged view
-        # d_full.view(world, max_cnt)[r, :gather_sizes[r]] (padding stays zero)
-        d_slot = torch.zeros(max_cnt, dtype=torch.float64, device="cuda")
-        d_probs = d_slot[:cnt]
-        d_full = torch.zeros(world * max_cnt, dtype=torch.float64, device="cuda") if world > 1 else None
+        d_slot = [torch.zeros(slot_len[j], dtype=torch.float64, device="cuda") for j in range(SUB)]
+        d_full = [torch.zeros(world * slot_len[j], dtype=torch.float64, device="cuda") for j in range(SUB)] if world > 1 else None
         d_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    d_probs = d_slot[0][:cnt] if SUB == 1 else None
+    comm_stream = torch.cuda.Stream() if world > 1 else None
 
     def device_step():
-        ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
-        if world > 1:
-            dist.all_gather_into_tensor(d_full, d_slot)
-            torch.sum(d_probs, dim=0, keepdim=True, out=d_sum)
-            dist.all_reduce(d_sum)
+        if world == 1:
+            ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
+            return
+        works = []
+        d_sum.zero_()
+        for j in range(SUB):
+            a, b = pieces[rank][j]
+            ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, a, b - a, d_slot[j])
+            d_sum.add_(d_slot[j].sum())
+            comm_stream.wait_stream(stream)
+            with torch.cuda.stream(comm_stream):
+                works.append(dist.all_gather_into_tensor(d_full[j], d_slot[j], async_op=True))
+        with torch.cuda.stream(comm_stream):
+            works.append(dist.all_reduce(d_sum, async_op=True))
+        for w in works:
+            w.wait()
+        stream.wait_stream(comm_stream)
 
     # pinned host buffers for the end-to-end leg
     h_U = torch.from_numpy(U.copy()).pin_memory()  # noqa: N806
@@ -349,6 +364,9 @@ def main() -> int:  # noqa: PLR0915
     launches = ctx.launch_count() - l0
     dev_ms = max_over_ranks(dev_ms)
     total_sum = float(d_probs.sum()) if world == 1 else float(d_sum)
+    if world > 1:
+        gathered = sum(float(t.sum()) for t in d_full)
+        assert abs(gathered - total_sum) < 1e-9, (gathered, total_sum)  # every rank holds the whole distribution
     value = S * args.steps / (dev_ms * 1e-3)
 
     # ---- end-to-end through the host-buffer C ABI ----
@@ -368,6 +386,10 @@ def main() -> int:  # noqa: PLR0915
     # `achieved` is ALGORITHMIC flops (2^(n-1)(8n-4) per permanent) over the kernel time for both;
     # `executed_frac` counts the FP64 work K1x really issues (terms x (8n-2)).
     peak = ctx.fp64_peak()  # measured live: MEASURED_PEAKS.json carries no FP64 entry
+
+    if d_probs is None:
+        with torch.cuda.stream(stream):
+            d_probs = torch.empty(cnt, dtype=torch.float64, device="cuda")
 
     def kernel_ms(reps=3):
         with torch.cuda.stream(stream):
@@ -421,7 +443,7 @@ def main() -> int:  # noqa: PLR0915
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128", "data": "synthetic",
         "config": {"workload": WORKLOAD, "modes": M, "photons": N_PH, "outputs": S,
-                   "parallelism": f"fock-rank-range shards x{world}" + (" + NCCL all-gather/all-reduce" if world > 1 else ""),
+                   "parallelism": f"fock-rank-range shards x{world} (equal work)" + (f" in {SUB} pieces, NCCL all-gather of piece j overlapped with the kernel of piece j+1, all-reduce of the sum" if world > 1 else ""),
                    "l2": "256 MiB flush between timed steps (outside the event pairs); outputs 740 MB > 126 MB L2",
                    "check_sum_of_probabilities": total_sum},
         "roofline": roofline, "roofline_expanded_rows": roofline_plain,
