@@ -312,3 +312,40 @@ def test_multiplicity_aware_equals_expanded(ctx, lb, m, n, seed):
     assert rel_close(fast, plain, 1e-10, 1e-18)
     ref = O.basis_probabilities(U, ins, r0, min(cnt, 500), threads=8)
     assert rel_close(fast[: len(ref)], ref, REL128, 1e-18)
+
+
+# ---------------------------------------------------------------- BASELINE configs 4 and 5 at full size
+def test_c4_noise_model_hot_path_properties(ctx, lb):
+    """C4: 16 modes, input |1^8,0^8>; an imperfect source turns into full_probability_distribution
+    calls for photon SUBSETS of the input.  For a spread of subsets: normalisation, permanent == SLOS on every output,
+    and the loss-free distribution through lwb_pdist equals the filtered basis probabilities in dict order."""
+    U = O.random_unitary(16, 4)  # noqa: N806
+    for bits in (0b11111111, 0b10110101, 0b00011000, 0b01111111, 0b00000001):
+        ins = [(bits >> i) & 1 for i in range(8)] + [0] * 8
+        n = sum(ins)
+        p = ctx.perm_basis_probs(U, ins)
+        assert len(p) == lb.fock_count(16, n)
+        assert abs(p.sum() - 1) < 1e-10
+        s = ctx.slos_basis_probs(U, ins, order=0)
+        big = p > 1e-12
+        assert rel_close(s[big], p[big], 1e-8)
+        assert np.max(np.abs(s - p)) < 1e-16
+        keys, vals = ctx.pdist(U, 16, ins, 1e-9, 0)
+        keep = p > 1e-9
+        assert np.array_equal(vals, p[keep])
+        if n <= 2:
+            assert np.array_equal(keys, ctx.fock_basis(16, n)[keep])
+
+
+def test_c5_single_permanent_slices_n28(ctx):
+    """C5: one 28 x 28 permanent of the 60-mode Haar unitary (seed 5); the Gray-code space split over 1/2/4/8
+    ranks gives the same value (up to summation order), and the complex64 variant agrees to its tolerance."""
+    A = O.random_unitary(60, 5)[:28, :28]  # noqa: N806
+    whole = ctx.perm_single(A)
+    for world in (2, 4, 8):
+        parts = sum(ctx.perm_single(A, slice_=r, n_slices=world) for r in range(world))
+        assert abs(parts - whole) <= 1e-10 * abs(whole)
+    # scaling a row by c scales the permanent by c (size-independent property)
+    B = A.copy()  # noqa: N806
+    B[3] *= (0.5 - 2j)
+    assert abs(ctx.perm_single(B) - whole * (0.5 - 2j)) <= 1e-9 * abs(whole) * 2.1
