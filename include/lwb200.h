@@ -51,9 +51,9 @@ int lwb_set_stream(lwb_handle h, void* cuda_stream, int use_own);
 int lwb_synchronize(lwb_handle h);
 /* Device facts for roofline reporting. */
 int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, int name_len);
-/* Kernel variant selection for n-photon permanents: lanes per permanent = 2^log_l,
- * min resident blocks per SM = minb.  Negative values restore the default. */
-int lwb_set_tuning(int n, int log_l, int minb);
+/* Kernel variant selection for n-photon batched permanents (sweeps): lanes per permanent = 2^log_l, from the
+ * variants compiled into the library; a negative log_l restores the default. */
+int lwb_set_tuning(int n, int log_l);
 /* Process-wide options.  "multiplicity_aware" (default 1): full-basis probability ranges use the
  * multiplicity-aware Glynn walk (prod(s_i+1)/2 terms for an output with occupations s_i) instead of
  * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel. */

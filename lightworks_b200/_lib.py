@@ -42,7 +42,7 @@ SIGNATURES = {
     "lwb_set_stream": (_i, [_vp, _vp, _i]),
     "lwb_synchronize": (_i, [_vp]),
     "lwb_device_info": (_i, [_vp, _pi, _pi, C.c_char_p, _i]),
-    "lwb_set_tuning": (_i, [_i, _i, _i]),
+    "lwb_set_tuning": (_i, [_i, _i]),
     "lwb_set_option": (_i, [C.c_char_p, _i]),
     "lwb_multiplicity_plan": (_i, [_i, _i, _pi, _pi, _pi, _pi, _pi, _pdbl]),
     "lwb_launch_count": (_i, [_vp, _pu64]),
@@ -379,5 +379,5 @@ def multiplicity_plan(n: int) -> list[dict]:
             return out
 
 
-def set_tuning(n: int, log_l: int = -1, minb: int = -1):
-    check(cdll().lwb_set_tuning(n, log_l, minb))
+def set_tuning(n: int, log_l: int = -1):
+    check(cdll().lwb_set_tuning(n, log_l))

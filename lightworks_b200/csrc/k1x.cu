@@ -174,8 +174,11 @@ struct K1xArgs {
     double* probs;
 };
 
+#ifndef K1X_MINB
+#define K1X_MINB 1
+#endif
 template <int N>
-__global__ void __launch_bounds__(K1X_THREADS) k1x_kernel(K1xArgs a) {
+__global__ void __launch_bounds__(K1X_THREADS, K1X_MINB) k1x_kernel(K1xArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = N | 1;  // odd row stride (in 16-byte units): lanes reading different rows spread over the banks
     double2* Vs = reinterpret_cast<double2*>(smem_raw);                  // [m][NP]
@@ -265,7 +268,6 @@ __global__ void __launch_bounds__(K1X_THREADS) k1x_kernel(K1xArgs a) {
         sr = fma(st.coef, pr, sr);
         si = fma(st.coef, pi, si);
         // v_slot += dir  =>  (s - 2v)/2 decreases by dir   (the update after the last term is harmless)
-        const double sg = st.dir > 0 ? -1.0 : 1.0;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
 #if K1X_EARLY_LOADS
@@ -277,7 +279,6 @@ __global__ void __launch_bounds__(K1X_THREADS) k1x_kernel(K1xArgs a) {
             if (st.dir > 0) { wr[j] -= v.x; wi[j] -= v.y; }
             else { wr[j] += v.x; wi[j] += v.y; }
         }
-        (void)sg;
         st = nx;
         rowaddr = nrowaddr;
     }

@@ -198,8 +198,7 @@ int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, 
     return 0;
 }
 
-int lwb_set_tuning(int n, int log_l, int minb) {
-    (void)minb;
+int lwb_set_tuning(int n, int log_l) {
     load_tables();
     if (n < 1 || n > LWB_K1_MAX_N) return fail(LWB_E_ARG, "lwb_set_tuning: n=%d", n);
     if (log_l >= 0) {

@@ -39,13 +39,18 @@ def main(argv=None) -> int:
     argv = [a for a in argv if a != "--b200"]
     from oracle import refshim
 
-    root = os.path.join(refshim.REFERENCE_ROOT, "tests", "emulator")
-    targets = [a for a in argv if not a.startswith("-")] or [root]
-    flags = [a for a in argv if a.startswith("-")]
+    tests_root = os.path.join(refshim.REFERENCE_ROOT, "tests")
+    # arguments naming a directory/file under the reference's tests/ (e.g. "qubit/gate_test.py") become targets,
+    # everything else is passed to pytest unchanged
+    targets, rest = [], []
+    for a in argv:
+        cand = a if os.path.isabs(a) else os.path.join(tests_root, a)
+        (targets if (not a.startswith("-") and os.path.exists(cand)) else rest).append(cand if os.path.exists(cand) and not a.startswith("-") else a)
+    targets = targets or [os.path.join(tests_root, "emulator")]
     with tempfile.TemporaryDirectory() as tmp:
         return pytest.main(
             [*targets, "-q", "-p", "no:cacheprovider", f"--rootdir={tmp}", "-c", os.devnull,
-             "-W", "ignore", *flags],
+             "-W", "ignore", *rest],
             plugins=[_ShimPlugin(b200)],
         )
 

@@ -124,3 +124,13 @@ def test_reference_emulator_suite_runs_on_b200():
                        capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
+
+
+def test_reference_qubit_and_tomography_suites_run_on_b200():
+    """Indirect consumers of the hot path: the reference's qubit gate tests (Simulator on the
+    permanent backend) and state / process tomography tests (Samplers on the slos backend), backends redirected."""
+    r = subprocess.run([sys.executable, "-m", "oracle.run_reference_tests", "--b200", "qubit/gate_test.py",
+                        "tomography/state_test.py", "tomography/process_test.py", "-k", "not plot", "-x"],
+                       cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    tail = (r.stdout + r.stderr)[-3000:]
+    assert r.returncode == 0, tail
