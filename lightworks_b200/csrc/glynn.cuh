@@ -106,6 +106,9 @@ __device__ __forceinline__ void row_fma(T (&wr)[N], T (&wi)[N], const typename v
     }
 }
 
+// (Dynamic flips multiply the row by a +-1.0 sign with a DFMA.  Branching to the 2-operand add / subtract forms
+// for warp-uniform signs was measured SLOWER on B200 - it splits the unrolled block and ptxas schedules worse.)
+
 // One chunk of 2^C Gray steps.
 //   rows   : shared-memory row table (row r starts at rows + r*N)
 //   rowidx : shared memory, N ints: rowidx[i] = (table row of matrix row i) * N
@@ -161,7 +164,8 @@ __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __rest
                     if (newbit) row_addsub<N, T, true>(wr, wi, lowrow[k]);
                     else row_addsub<N, T, false>(wr, wi, lowrow[k]);
                 } else {
-                    // k == U-1 (middle of the block): bit U of the global index decides
+                    // k == U-1 (middle of the block): bit U of the global index decides.  (A branch to the add/sub
+                    // forms for the warp-uniform case was measured SLOWER here: it splits the unrolled block.)
                     const uint32_t hi = (U == C) ? (q & 1u) : (ob & 1u);
                     row_fma<N, T>(wr, wi, lowrow[k], hi ? T(1) : T(-1));  // newbit = 1 ^ hi
                 }

@@ -9,6 +9,7 @@ from lightworks_b200 import _lib as L  # noqa: E402
 from oracle import oracle as O  # noqa: E402, N812
 
 ctx = L.Context(0)
+L.set_option("multiplicity_aware", 0)  # this tool times the expanded-row kernel variants
 stream = torch.cuda.Stream()
 ctx.set_stream(stream.cuda_stream)
 PEAK = float(os.environ.get("FP64_PEAK", "36.07e12"))
