@@ -474,11 +474,14 @@ int lwb_perm_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in
     CK(ensure(h, h->bRes, cnt * 8));
     CU(cudaMemcpyAsync(h->bU.p, U, (size_t)m * m * 16, cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->bIn.p, in_state, (size_t)m, cudaMemcpyHostToDevice, h->stream));
-    // Large ranges are cut into chunks so the device-to-host copy of chunk c overlaps the kernel of chunk c+1
-    // (the copy is the only host<->device traffic of this path: 8 bytes per state).
-    const int chunks = cnt >= (4u << 20) ? 8 : 1;
+    // Large ranges are cut into a few pieces of decreasing size so the device-to-host copy of piece c overlaps the
+    // kernels of piece c+1 and only the small last copy is exposed (the copy is the only host<->device traffic of
+    // this path: 8 bytes per state).  Few pieces: every piece pays the bucketing passes of the multiplicity-aware walk.
+    static const double cut[5] = {0.0, 0.40, 0.70, 0.90, 1.0};
+    const int chunks = cnt >= (4u << 20) ? 4 : 1;
     for (int c = 0; c < chunks; ++c) {
-        const uint64_t b = cnt * (uint64_t)c / chunks, e = cnt * (uint64_t)(c + 1) / chunks;
+        const uint64_t b = chunks == 1 ? 0 : (uint64_t)((double)cnt * cut[c]);
+        const uint64_t e = chunks == 1 ? cnt : (c + 1 == chunks ? cnt : (uint64_t)((double)cnt * cut[c + 1]));
         CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, 1, nullptr, r0 + b, e - b, n, dtype, 1,
                          (double*)h->bRes.p + b));
         if (chunks == 1) {
