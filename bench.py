@@ -423,7 +423,7 @@ def main() -> int:  # noqa: PLR0915
             traffic = None
     peak_src = ("lwb_fp64_peak DFMA micro-benchmark run inside this bench (MEASURED_PEAKS.json has no FP64 entry; nominal "
                 "148 SM x 64 DFMA/clk x 2 x 1.965 GHz = 37.2 TFLOP/s)")
-    roofline = {"bound": "fp64", "kernel": "k1x_kernel<N=10> + bucketing passes (multiplicity-aware Glynn/Gray walk)",
+    roofline = {"bound": "fp64", "kernel": "k1x_fused_kernel_2<N=10> + bucketing passes (multiplicity-aware Glynn/Gray walk, one launch for all patterns)",
                 "achieved": alg / (k_ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                 "frac": alg / (k_ms * 1e-3) / peak, "executed_frac": executed / (k_ms * 1e-3) / peak,
                 "average_terms_per_permanent": avg_terms, "terms_expanded": 2 ** (N_PH - 1),

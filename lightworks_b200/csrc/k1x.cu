@@ -11,37 +11,9 @@
 #include "../../include/lwb200.h"
 #include "fock.cuh"
 #include "glynn.cuh"
+#include "k1x_common.cuh"
 
 namespace lwb {
-
-#ifndef K1X_UNROLL
-#define K1X_UNROLL 2
-#endif
-#ifndef K1X_EARLY_LOADS
-#define K1X_EARLY_LOADS 1
-#endif
-constexpr int k1x_unroll = K1X_UNROLL;
-constexpr int K1X_THREADS = 256;
-constexpr int K1X_MAX_N = 16;       // kernels instantiated for 2 <= n <= 16
-constexpr int K1X_CL_THREADS = 1024;  // one state per thread in the bucketing passes
-constexpr int K1X_MAX_TYPES = 256;    // partitions of n: p(16) = 231
-
-struct TypeMeta {
-    int d;         // distinct rows
-    int T;         // terms of the walk
-    int prog_off;  // first Step of this type in the program array
-    int factor;    // 2 when the v -> s-v symmetry halves the sum, else 1
-    int s[K1X_MAX_N];  // multiplicities, descending
-};
-struct Step {
-    double coef;  // (-1)^{sum v} prod C(s_i, v_i) of the tuple BEFORE the transition
-    int slot;     // row slot whose v changes after this term (unused for the last term)
-    int dir;      // +1 / -1
-};
-struct BlockWork {
-    int type;
-    uint32_t begin, end;  // range of bucket entries
-};
 
 // ---- type key: parts >= 2 of the partition, descending, 5 bits each ------------------------------------
 __host__ __device__ inline uint64_t pack_key(const int* parts_desc, int count) {
@@ -161,129 +133,31 @@ __global__ void __launch_bounds__(1024) k1x_scan_kernel(uint32_t* H, uint32_t nb
     if (threadIdx.x == 1023) totals[blockIdx.x] = part[1023];
 }
 
-struct K1xArgs {
-    const uint64_t* bin;
-    const double2* U;
-    int m;
-    const uint8_t* in_state;
-    uint64_t r0;
-    const TypeMeta* meta;
-    const Step* prog;
-    const BlockWork* work;
-    const uint32_t* bucket;
-    double* probs;
-};
-
-// (no minBlocks in the launch bounds: with an explicit 1 ptxas schedules this loop ~25 % slower on B200)
-template <int N>
-__global__ void __launch_bounds__(K1X_THREADS) k1x_kernel(K1xArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NP = N | 1;  // odd row stride (in 16-byte units): lanes reading different rows spread over the banks
-    double2* Vs = reinterpret_cast<double2*>(smem_raw);                  // [m][NP]
-    int* srow = reinterpret_cast<int*>(Vs + (size_t)a.m * NP);           // [N][K1X_THREADS] row offsets per slot
-    __shared__ int incol[N];
-    __shared__ double fin_s;
-    __shared__ TypeMeta tm;
-    const int tid = threadIdx.x;
-    const int m = a.m;
-    const BlockWork bw = a.work[blockIdx.x];
-    if (tid == 0) {
-        int c = 0;
-        double f = 1.0;
-        for (int i = 0; i < m; ++i)
-            for (int k = 0; k < a.in_state[i]; ++k) {
-                if (c < N) incol[c] = i;
-                ++c;
-                f *= (double)(k + 1);
-            }
-        fin_s = f;
-        tm = a.meta[bw.type];
-    }
+// Bucket layout from the per-type totals: exclusive scans, in layout order, of the state counts (-> offsets[type])
+// and of the block counts ceil(count / threads per block) (-> bstart[position]); one block, thread <-> layout position.
+__global__ void __launch_bounds__(K1X_MAX_TYPES) k1x_layout_kernel(const unsigned int* counts, const int* layout,
+                                                                     int n_types, uint32_t threads, uint32_t* offsets,
+                                                                     uint32_t* bstart) {
+    __shared__ uint32_t so[K1X_MAX_TYPES], sb[K1X_MAX_TYPES];
+    const int p = threadIdx.x;
+    const int type = p < n_types ? layout[p] : 0;
+    const uint32_t c = p < n_types ? counts[type] : 0u;
+    const uint32_t nb = (c + threads - 1) / threads;
+    so[p] = c;
+    sb[p] = nb;
     __syncthreads();
-    for (int e = tid; e < m * N; e += K1X_THREADS) {
-        const int r = e / N, c = e - r * N;
-        Vs[r * NP + c] = a.U[(size_t)r * m + incol[c]];
+    for (int off = 1; off < K1X_MAX_TYPES; off <<= 1) {
+        const uint32_t vo = p >= off ? so[p - off] : 0u, vb = p >= off ? sb[p - off] : 0u;
+        __syncthreads();
+        so[p] += vo;
+        sb[p] += vb;
+        __syncthreads();
     }
-    __syncthreads();
-    const uint32_t item = bw.begin + tid;
-    if (item >= bw.end) return;
-    const uint32_t k = a.bucket[item];
-
-    // this thread's output state -> distinct modes ordered by decreasing multiplicity (= the type's slot order)
-    const int d = tm.d;
-    double fout = 1.0;
-    {
-        int x[N];
-        colex_unrank(a.bin, a.r0 + k, N, m, x);
-        int mode[N], mult[N];
-        int nd = 0, run = 1;
-        for (int i = 1; i <= N; ++i) {
-            if (i < N && x[i] == x[i - 1]) { ++run; fout *= (double)run; continue; }
-            int p = nd++;
-            while (p > 0 && mult[p - 1] < run) { mult[p] = mult[p - 1]; mode[p] = mode[p - 1]; --p; }
-            mult[p] = run;
-            mode[p] = x[i - 1];
-            run = 1;
-        }
-        for (int sl = 0; sl < nd; ++sl) srow[sl * K1X_THREADS + tid] = mode[sl] * NP;
+    if (p < n_types) {
+        offsets[type] = so[p] - c;
+        bstart[p] = sb[p] - nb;
+        if (p == n_types - 1) bstart[n_types] = sb[p];
     }
-
-    // start tuple v = 0:  w_j = 1/2 sum_i s_i a_{r_i j}
-    double wr[N], wi[N];
-#pragma unroll
-    for (int j = 0; j < N; ++j) { wr[j] = 0.0; wi[j] = 0.0; }
-    for (int sl = 0; sl < d; ++sl) {
-        const double c = 0.5 * (double)tm.s[sl];
-        const double2* row = Vs + srow[sl * K1X_THREADS + tid];
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            const double2 v = lds_c(row, j);
-            wr[j] = fma(c, v.x, wr[j]);
-            wi[j] = fma(c, v.y, wi[j]);
-        }
-    }
-    const Step* prog = a.prog + tm.prog_off;
-    const int T = tm.T;
-    double sr = 0.0, si = 0.0;
-    // The step descriptor and this lane's row address are fetched one term ahead, and the row of a flip is
-    // loaded BEFORE the product chain of the same term, so the shared-memory latency hides behind ~40 FP64
-    // instructions instead of stalling the adds.
-    const uint32_t vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
-    Step st = prog[0];  // same address for every lane of the block: one broadcast load
-    uint32_t rowaddr = vs_base + 16u * (uint32_t)srow[st.slot * K1X_THREADS + tid];
-#pragma unroll k1x_unroll
-    for (int t = 0; t < T; ++t) {
-        const Step nx = prog[t + 1 < T ? t + 1 : t];
-        const uint32_t nrowaddr = vs_base + 16u * (uint32_t)srow[nx.slot * K1X_THREADS + tid];
-#if K1X_EARLY_LOADS
-        double2 rv[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(rv[j].x), "=d"(rv[j].y) : "r"(rowaddr + 16u * j));
-#endif
-        double pr, pi;
-        cprod<N, double>(wr, wi, pr, pi);
-        sr = fma(st.coef, pr, sr);
-        si = fma(st.coef, pi, si);
-        // v_slot += dir  =>  (s - 2v)/2 decreases by dir   (the update after the last term is harmless)
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-#if K1X_EARLY_LOADS
-            const double2 v = rv[j];
-#else
-            double2 v;
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(rowaddr + 16u * j));
-#endif
-            if (st.dir > 0) { wr[j] -= v.x; wi[j] -= v.y; }
-            else { wr[j] += v.x; wi[j] += v.y; }
-        }
-        st = nx;
-        rowaddr = nrowaddr;
-    }
-    const double scale = sqrt(fin_s * fout);
-    const double f = (double)tm.factor;
-    const double re = (f * sr) / scale, im = (f * si) / scale;
-    a.probs[k] = re * re + im * im;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -295,7 +169,7 @@ struct Plan {
     int* d_key_type = nullptr;
     TypeMeta* d_meta = nullptr;
     Step* d_prog = nullptr;
-    std::vector<int> order_by_T;  // type ids, heaviest first
+    int* d_layout = nullptr;  // type ids, heaviest first: the order of the buckets and of the blocks
 };
 
 struct K1xState {
@@ -305,10 +179,9 @@ struct K1xState {
     size_t H_cap = 0;
     unsigned char* d_types = nullptr;
     uint32_t* d_offsets = nullptr;
+    uint32_t* d_bstart = nullptr;
     uint32_t* d_bucket = nullptr;
     size_t bucket_cap = 0;
-    BlockWork* d_work = nullptr;
-    size_t work_cap = 0;
 };
 
 K1xState* k1x_create() { return new K1xState(); }
@@ -320,20 +193,21 @@ void k1x_destroy(K1xState* st) {
         cudaFree(kv.second.d_key_type);
         cudaFree(kv.second.d_meta);
         cudaFree(kv.second.d_prog);
+        cudaFree(kv.second.d_layout);
     }
     cudaFree(st->d_counts);
     cudaFree(st->d_H);
     cudaFree(st->d_types);
     cudaFree(st->d_offsets);
+    cudaFree(st->d_bstart);
     cudaFree(st->d_bucket);
-    cudaFree(st->d_work);
     delete st;
 }
 
 bool k1x_supported(int n) { return n >= 2 && n <= K1X_MAX_N; }
 
 static void partitions(int n, int maxpart, std::vector<int>& cur, std::vector<std::vector<int>>& out);
-static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<Step>& prog);
+static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<Step>& prog, bool allow_static);
 
 // Host-only description of the walk programs for n photons (no device needed): number of multiplicity patterns,
 // and for pattern index t (partitions of n in descending lexicographic order) its multiplicities, term count,
@@ -347,7 +221,7 @@ int k1x_plan_info(int n, int t, int* n_types, int* s_out, int* d_out, int* T_out
     if (t < 0 || t >= (int)parts.size()) return LWB_E_ARG;
     TypeMeta tm;
     std::vector<Step> prog;
-    build_program(parts[t], tm, prog);
+    build_program(parts[t], tm, prog, false);
     for (int i = 0; i < tm.d; ++i) s_out[i] = tm.s[i];
     *d_out = tm.d;
     *T_out = tm.T;
@@ -373,16 +247,30 @@ static double binom_d(int a, int b) {
     return std::floor(r + 0.5);
 }
 
-// reflected mixed-radix Gray walk (Knuth 7.2.1.1 Algorithm H) over the digits with radix > 1
-static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<Step>& prog) {
+// reflected mixed-radix Gray walk (Knuth 7.2.1.1 Algorithm H) over the digits with radix > 1.
+// Generic program (klass -1): every tuple of every row is a Step.  Static program (>= 3 single rows): only the
+// bunched rows are digits; each Step stands for a whole binary Gray chunk over C = ns - 1 single rows, and its
+// coefficient also carries the sign of the chunk's first term (the chunk parity alternates with the step index).
+static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<Step>& prog, bool allow_static = true) {
     const int d = (int)s.size();
+    int ns = 0;
+    for (int v : s) ns += (v == 1);
+    const bool is_static = allow_static && ns >= 3;
     std::vector<int> R(d);
-    int h = -1;
-    for (int i = d - 1; i >= 0; --i)
-        if (s[i] % 2 == 1) { h = i; break; }
     for (int i = 0; i < d; ++i) R[i] = s[i] + 1;
     tm.factor = 1;
-    if (h >= 0) { R[h] = (s[h] + 1) / 2; tm.factor = 2; }
+    tm.ns = ns;
+    tm.klass = is_static ? ns - 1 : -1;
+    if (is_static) {
+        for (int i = 0; i < d; ++i)
+            if (s[i] == 1) R[i] = 1;  // single rows are walked by the unrolled binary chunk
+        tm.factor = 2;                // ... one of them fixed to '+'
+    } else {
+        int h = -1;
+        for (int i = d - 1; i >= 0; --i)
+            if (s[i] % 2 == 1) { h = i; break; }
+        if (h >= 0) { R[h] = (s[h] + 1) / 2; tm.factor = 2; }
+    }
     // fastest Gray digit = last slot: among equal multiplicities the slots are in ascending mode order and, in
     // the reference's rank order, high modes change slowest from one state to the next, so the rows flipped most
     // often are the ones neighbouring lanes share
@@ -401,6 +289,7 @@ static void build_program(const std::vector<int>& s, TypeMeta& tm, std::vector<S
         double coef = 1.0;
         int sum = 0;
         for (int i = 0; i < d; ++i) { coef *= binom_d(s[i], v[i]); sum += v[i]; }
+        if (is_static) sum += T & 1;  // chunk T starts from the pattern with (T & 1) single rows negated
         Step st;
         st.coef = (sum & 1) ? -coef : coef;
         st.slot = 0;
@@ -433,7 +322,7 @@ static int make_plan(K1xState* st, int n, Plan** out, std::string* err) {
     std::vector<std::pair<uint64_t, int>> keyed;
     pl.meta.resize(pl.n_types);
     for (int t = 0; t < pl.n_types; ++t) {
-        build_program(parts[t], pl.meta[t], prog);
+        build_program(parts[t], pl.meta[t], prog, n >= K1X_STATIC_MIN_N);
         int big[K1X_MAX_N];
         int nb = 0;
         for (int p : parts[t])
@@ -444,9 +333,16 @@ static int make_plan(K1xState* st, int n, Plan** out, std::string* err) {
     std::vector<uint64_t> keys;
     std::vector<int> key_type;
     for (auto& kv : keyed) { keys.push_back(kv.first); key_type.push_back(kv.second); }
-    pl.order_by_T.resize(pl.n_types);
-    for (int t = 0; t < pl.n_types; ++t) pl.order_by_T[t] = t;
-    std::sort(pl.order_by_T.begin(), pl.order_by_T.end(), [&](int x, int y) { return pl.meta[x].T > pl.meta[y].T; });
+    std::vector<int> layout(pl.n_types);
+    for (int t = 0; t < pl.n_types; ++t) layout[t] = t;
+    auto terms = [&](int t) { return (double)pl.meta[t].T * (pl.meta[t].klass >= 0 ? (double)(1 << pl.meta[t].klass) : 1.0); };
+#ifdef K1X_LAYOUT_BY_CLASS
+    std::stable_sort(layout.begin(), layout.end(), [&](int x, int y) {
+        return pl.meta[x].klass != pl.meta[y].klass ? pl.meta[x].klass > pl.meta[y].klass : terms(x) > terms(y);
+    });
+#else
+    std::stable_sort(layout.begin(), layout.end(), [&](int x, int y) { return terms(x) > terms(y); });
+#endif
 #define K1X_CU(call)                                                                  \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
@@ -456,6 +352,8 @@ static int make_plan(K1xState* st, int n, Plan** out, std::string* err) {
     K1X_CU(cudaMalloc(&pl.d_key_type, key_type.size() * 4));
     K1X_CU(cudaMalloc(&pl.d_meta, pl.meta.size() * sizeof(TypeMeta)));
     K1X_CU(cudaMalloc(&pl.d_prog, prog.size() * sizeof(Step)));
+    K1X_CU(cudaMalloc(&pl.d_layout, layout.size() * 4));
+    K1X_CU(cudaMemcpy(pl.d_layout, layout.data(), layout.size() * 4, cudaMemcpyHostToDevice));
     K1X_CU(cudaMemcpy(pl.d_keys, keys.data(), keys.size() * 8, cudaMemcpyHostToDevice));
     K1X_CU(cudaMemcpy(pl.d_key_type, key_type.data(), key_type.size() * 4, cudaMemcpyHostToDevice));
     K1X_CU(cudaMemcpy(pl.d_meta, pl.meta.data(), pl.meta.size() * sizeof(TypeMeta), cudaMemcpyHostToDevice));
@@ -465,10 +363,9 @@ static int make_plan(K1xState* st, int n, Plan** out, std::string* err) {
     return 0;
 }
 
-typedef void (*K1xFn)(K1xArgs);
 template <int N>
-struct K1xTable {
-    static void fill(K1xFn* t) { t[N] = k1x_kernel<N>; K1xTable<N - 1>::fill(t); }
+struct K1xTable {  // n below the static range: the generic walk only
+    static void fill(K1xFn* t) { t[N] = k1x_fused_kernel<N, false>; K1xTable<N - 1>::fill(t); }
 };
 template <>
 struct K1xTable<1> {
@@ -480,8 +377,17 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
                     std::string* err) {
     static K1xFn table[K1X_MAX_N + 1];
     static bool table_init = false;
-    if (!table_init) { K1xTable<K1X_MAX_N>::fill(table); table_init = true; }
-    if (!k1x_supported(n) || cnt >= (1ull << 32)) { *err = "k1x: unsupported size"; return LWB_E_LIMIT; }
+    if (!table_init) {
+        K1xTable<K1X_STATIC_MIN_N - 1>::fill(table);
+        const K1xStaticEntry* (*groups[])(int*) = LWB_K1XS_GROUPS;
+        for (auto g : groups) {
+            int c = 0;
+            const K1xStaticEntry* e = g(&c);
+            for (int i = 0; i < c; ++i) table[e[i].n] = e[i].fn;
+        }
+        table_init = true;
+    }
+    if (!k1x_supported(n) || !table[n] || cnt >= (1ull << 32)) { *err = "k1x: unsupported size"; return LWB_E_LIMIT; }
     if (cnt == 0) return 0;
     Plan* pl = nullptr;
     int rc = make_plan(st, n, &pl, err);
@@ -489,6 +395,7 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
     if (!st->d_counts) {
         K1X_CU(cudaMalloc(&st->d_counts, K1X_MAX_TYPES * 4));
         K1X_CU(cudaMalloc(&st->d_offsets, K1X_MAX_TYPES * 4));
+        K1X_CU(cudaMalloc(&st->d_bstart, (K1X_MAX_TYPES + 1) * 4));
     }
     if (st->bucket_cap < cnt) {
         if (st->d_bucket) K1X_CU(cudaFree(st->d_bucket));
@@ -499,7 +406,7 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
         K1X_CU(cudaMalloc(&st->d_types, cnt));
         st->bucket_cap = cnt;
     }
-    // pass 1: per-block counts, then per-type exclusive scan over the blocks (device) and totals (host)
+    // pass 1: per-block counts; per-type exclusive scan over the blocks and totals; bucket/block layout
     const uint32_t nb = (uint32_t)((cnt + K1X_CL_THREADS - 1) / K1X_CL_THREADS);
     const size_t h_entries = (size_t)pl->n_types * nb;
     if (st->H_cap < h_entries) {
@@ -513,48 +420,24 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
     ca.n_types = pl->n_types; ca.nb = nb; ca.H = st->d_H; ca.offsets = st->d_offsets; ca.bucket = st->d_bucket; ca.types = st->d_types; ca.fill = 0;
     k1x_classify_kernel<K1X_MAX_N><<<nb, K1X_CL_THREADS, 0, stream>>>(ca);
     k1x_scan_kernel<<<pl->n_types, 1024, 0, stream>>>(st->d_H, nb, st->d_counts);
-    *launches += 2;
-    std::vector<unsigned int> counts(pl->n_types);
-    K1X_CU(cudaMemcpyAsync(counts.data(), st->d_counts, pl->n_types * 4, cudaMemcpyDeviceToHost, stream));
-    K1X_CU(cudaStreamSynchronize(stream));
-    // bucket layout (heaviest types first) and the block work list
-    std::vector<uint32_t> offsets(pl->n_types, 0);
-    std::vector<BlockWork> work;
-    uint32_t off = 0;
-    for (int t : pl->order_by_T) {
-        offsets[t] = off;
-        for (uint32_t b = 0; b < counts[t]; b += K1X_THREADS) {
-            BlockWork w;
-            w.type = t;
-            w.begin = off + b;
-            w.end = off + std::min<uint32_t>(counts[t], b + K1X_THREADS);
-            work.push_back(w);
-        }
-        off += counts[t];
-    }
-    if (st->work_cap < work.size()) {
-        if (st->d_work) K1X_CU(cudaFree(st->d_work));
-        st->d_work = nullptr;
-        K1X_CU(cudaMalloc(&st->d_work, work.size() * sizeof(BlockWork)));
-        st->work_cap = work.size();
-    }
-    K1X_CU(cudaMemcpyAsync(st->d_offsets, offsets.data(), pl->n_types * 4, cudaMemcpyHostToDevice, stream));
-    K1X_CU(cudaMemcpyAsync(st->d_work, work.data(), work.size() * sizeof(BlockWork), cudaMemcpyHostToDevice, stream));
+    const int tb = k1x_threads(n);
+    k1x_layout_kernel<<<1, K1X_MAX_TYPES, 0, stream>>>(st->d_counts, pl->d_layout, pl->n_types, (uint32_t)tb, st->d_offsets, st->d_bstart);
     // pass 2: stable fill of the buckets
     ca.fill = 1;
     k1x_classify_kernel<K1X_MAX_N><<<nb, K1X_CL_THREADS, 0, stream>>>(ca);
-    ++*launches;
-    // main kernel: one block per 256 permanents of one type
+    // permanents: one block per tb permanents of one pattern; the grid is the upper bound
+    // sum_t ceil(count_t / tb) <= ceil(cnt / tb) + n_types  (the block table lives on the device)
     K1xArgs ka;
     ka.bin = d_bin; ka.U = d_U; ka.m = m; ka.in_state = d_in_state; ka.r0 = r0; ka.meta = pl->d_meta; ka.prog = pl->d_prog;
-    ka.work = st->d_work; ka.bucket = st->d_bucket; ka.probs = d_probs;
-    const size_t smem = (size_t)m * (n | 1) * 16 + (size_t)n * K1X_THREADS * 4;
+    ka.layout = pl->d_layout; ka.bstart = st->d_bstart; ka.offsets = st->d_offsets; ka.counts = st->d_counts;
+    ka.n_types = pl->n_types; ka.bucket = st->d_bucket; ka.probs = d_probs;
+    const size_t smem = (size_t)m * (n | 1) * 16 + (size_t)n * tb * 4;
     K1xFn fn = table[n];
     if (smem > 48 * 1024) K1X_CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    fn<<<(unsigned)work.size(), K1X_THREADS, smem, stream>>>(ka);
-    ++*launches;
+    const uint64_t grid = (cnt + tb - 1) / tb + (uint64_t)pl->n_types;
+    fn<<<(unsigned)grid, tb, smem, stream>>>(ka);
+    *launches += 5;
     K1X_CU(cudaGetLastError());
-    // (the host vectors above are pageable: cudaMemcpyAsync has staged them before returning)
     return 0;
 }
 

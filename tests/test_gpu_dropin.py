@@ -120,8 +120,12 @@ def test_sampler_cache_is_inherited(lw):
 def test_reference_emulator_suite_runs_on_b200():
     """The reference's own tests/emulator suite with Backend("permanent"/"slos"), PermanentBackend and
     SLOSBackend redirected to the B200 classes (SURVEY.md section 8d 'correctness gates')."""
-    r = subprocess.run([sys.executable, "-m", "oracle.run_reference_tests", "--b200", "-x"], cwd=ROOT,
-                       capture_output=True, text=True, timeout=1500)
+    # the reference marks its statistical sampling tests `flaky` (rerun plugin, absent here): one retry of the suite
+    for attempt in range(2):
+        r = subprocess.run([sys.executable, "-m", "oracle.run_reference_tests", "--b200", "-x"], cwd=ROOT,
+                           capture_output=True, text=True, timeout=1500)
+        if r.returncode == 0:
+            break
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
 
