@@ -523,7 +523,32 @@ def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
                       "roofline": {"bound": "hbm", "achieved": slos_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes},
                       "note": "SLOS backend, same distribution in SLOS dict order, all 10 layers"}
-    del d_p
+    # on-device sampling of the same distribution: CDF build + search, device-resident, and the
+    # whole Sampler chain through the host API (U in, 10^6 variates in, 10^6 drawn ranks out)
+    n_smp = 1_000_000
+    with torch.cuda.stream(stream):
+        ctx.perm_basis_probs_dev(d_U, M, torch.tensor(ins, dtype=torch.uint8, device="cuda"), N_PH, 0, S, d_p)
+        d_u = torch.rand(n_smp, dtype=torch.float64, device="cuda")
+        d_i = torch.empty(n_smp, dtype=torch.int64, device="cuda")
+    ms = t_ms(lambda: ctx.sample_dev(d_p, S, d_u, n_smp, d_i, threshold=1e-9))
+    scan_bytes = 24 * S  # two reads of the probabilities, one write of the CDF
+    u_host = np.random.default_rng(0).random(n_smp)
+    U_host = O.random_unitary(M, 3)  # noqa: N806
+    ctx.basis_sample(U_host, ins, u_host)
+    e2e_ms = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        ctx.basis_sample(U_host, ins, u_host)
+        e2e_ms = min(e2e_ms, 1e3 * (time.perf_counter() - t0))
+    out["sampler_c3_on_device"] = {"samples": n_smp, "cdf_and_search_ms": ms,
+                                   "roofline": {"bound": "hbm", "achieved": scan_bytes / (ms * 1e-3) / 1e9, "peak": hbm,
+                                                "unit": "GB/s", "frac": scan_bytes / (ms * 1e-3) / 1e9 / hbm,
+                                                "algorithmic_bytes": scan_bytes,
+                                                "note": "CDF of 92.6 M probabilities (24 B per state) + 10^6 binary searches"},
+                                   "e2e_ms": e2e_ms, "e2e_samples_per_s": n_smp / (e2e_ms * 1e-3),
+                                   "note": "lwb_basis_sample: distribution computed, thresholded, normalised and sampled on "
+                                           "the GPU; host traffic = U + 8 B per variate in, 8 B per sample out"}
+    del d_p, d_u, d_i
     for n, dt, name in ((12, _lib.LWB_C128, "c128"), (16, _lib.LWB_C128, "c128"), (20, _lib.LWB_C128, "c128"),
                         (12, _lib.LWB_C64, "c64")):
         B = int(max(2e11 / flops_per_perm(n), 148 * 64))  # noqa: N806

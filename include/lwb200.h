@@ -131,6 +131,23 @@ int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const 
               double threshold, int backend, int dtype, uint8_t* keys, double* vals, uint64_t cap,
               uint64_t* count_out);
 
+/* ---- on-device sampling ---------------------------------------------------------------------------
+ * SamplerRunner._gen_samples_from_dist (simulation/sampler.py:329-349): rng.choice(len(dist), p=probs, size=N),
+ * i.e. numpy's  cdf = cumsum(p) / sum(p); index = searchsorted(cdf, rng.random(N), side='right').
+ * The caller supplies the N uniform variates (numpy's Generator on the host keeps the reference's seeding);
+ * the CDF is built and searched on the device.  Entries with p <= threshold count as zero, which is how the
+ * reference's dict drops them (permanent.py:151, slos.py:74); pass a negative threshold to keep everything.
+ *   index[k] = position in `probs` drawn by uniform[k];  total (optional) = sum of the kept probabilities.
+ * lwb_basis_sample computes the full-basis distribution of one input state on the device (backend 0: permanent
+ * path, indices in fock_basis order; 1: SLOS path, indices in SLOS dict order) and samples it without the
+ * probabilities ever leaving the GPU: host traffic is m*m*16 + 8*N bytes in, 8*N + 8 bytes out. */
+int lwb_sample(lwb_handle h, const double* probs, uint64_t S, double threshold, const double* uniform,
+               uint64_t n_samples, uint64_t* index, double* total);
+int lwb_sample_dev(lwb_handle h, const double* d_probs, uint64_t S, double threshold, const double* d_uniform,
+                   uint64_t n_samples, uint64_t* d_index, double* d_total);
+int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
+                     const double* uniform, uint64_t n_samples, uint64_t* index, double* total);
+
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */
 int lwb_fp64_peak(lwb_handle h, double* flops_per_s);

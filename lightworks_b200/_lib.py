@@ -66,6 +66,9 @@ SIGNATURES = {
     "lwb_slos_basis_probs": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "lwb_slos_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp]),
     "lwb_pdist": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _i, _vp, _vp, _u64, _pu64]),
+    "lwb_sample": (_i, [_vp, _vp, _u64, _dbl, _vp, _u64, _vp, _pdbl]),
+    "lwb_sample_dev": (_i, [_vp, _vp, _u64, _dbl, _vp, _u64, _vp, _vp]),
+    "lwb_basis_sample": (_i, [_vp, _i, _vp, _i, _vp, _dbl, _vp, _u64, _vp, _pdbl]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
     "lwb_fp64_probe": (_i, [_vp, _i, _pdbl]),
 }
@@ -317,7 +320,34 @@ def _slos_methods():
         k = int(count.value)
         return keys[:k], vals[:k]
 
-    for f in (slos_amplitudes, slos_basis_probs, slos_basis_probs_dev, slos_amplitudes_dev, pdist):
+    def sample(self, probs, uniform, threshold=-1.0):
+        """numpy's Generator.choice(len(probs), p=probs / probs.sum(), size=len(uniform)) for caller-drawn uniform
+        variates (sampler.py:329-349): index drawn by every variate, and the sum of the kept probabilities."""
+        probs = np.ascontiguousarray(probs, dtype=np.float64)
+        uniform = np.ascontiguousarray(uniform, dtype=np.float64)
+        idx = np.zeros(len(uniform), dtype=np.uint64)
+        total = C.c_double(0)
+        check(cdll().lwb_sample(self._h, ptr(probs), len(probs), float(threshold), ptr(uniform), len(uniform), ptr(idx),
+                                C.byref(total)))
+        return idx, float(total.value)
+
+    def sample_dev(self, d_probs, S, d_uniform, n_samples, d_index, threshold=-1.0, d_total=None):  # noqa: N803
+        check(cdll().lwb_sample_dev(self._h, ptr(d_probs), S, float(threshold), ptr(d_uniform), n_samples, ptr(d_index),
+                                    ptr(d_total)))
+
+    def basis_sample(self, U, in_state, uniform, threshold=1e-9, backend=BACKEND_PERMANENT):  # noqa: N803
+        """Full-basis distribution of one input state computed AND sampled on the device: returns the drawn
+        positions (fock_basis ranks for the permanent backend, SLOS dict positions for slos) and sum(p)."""
+        U, s, _ = _prep(U, in_state)  # noqa: N806
+        uniform = np.ascontiguousarray(uniform, dtype=np.float64)
+        idx = np.zeros(len(uniform), dtype=np.uint64)
+        total = C.c_double(0)
+        check(cdll().lwb_basis_sample(self._h, backend, ptr(U), U.shape[0], ptr(s), float(threshold), ptr(uniform),
+                                      len(uniform), ptr(idx), C.byref(total)))
+        return idx, float(total.value)
+
+    for f in (slos_amplitudes, slos_basis_probs, slos_basis_probs_dev, slos_amplitudes_dev, pdist, sample, sample_dev,
+              basis_sample):
         setattr(Context, f.__name__, f)
 
 

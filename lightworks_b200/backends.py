@@ -89,6 +89,29 @@ class _B200Base:
         return self.ctx.pdist(U, circuit.n_modes, ins, _threshold(), backend_id, self._dtype)
 
 
+    _backend_id = _lib.BACKEND_PERMANENT
+
+    def sample_outputs(self, circuit, input_state, n_samples: int, seed=None) -> dict:
+        """On-device replacement of `Sampler(circuit, input_state, n_samples, random_seed=seed)` for the plain case
+        (perfect source, photon-counting ideal detector, no heralds / loss / post-selection): the chain
+        full_probability_distribution -> SamplerRunner._sample_N_outputs -> _gen_samples_from_dist
+        (simulation/sampler.py:240-349) with the distribution computed, thresholded, normalised and searched on the
+        GPU.  Only the n_samples uniform variates go in and the drawn positions come back; the variates come from
+        numpy's `default_rng(seed).random(n_samples)`, the stream `rng.choice` consumes, so a seed draws the same
+        states as the reference.  Returns {State: count} in first-drawn order (Counter semantics)."""
+        from collections import Counter
+
+        if getattr(circuit, "loss_modes", 0) or len(_as_list(input_state)) != circuit.n_modes:
+            raise ValueError("sample_outputs covers lossless circuits with a full-width input state")
+        ins = _as_list(input_state)
+        rng = np.random.default_rng(seed)
+        uniform = rng.random(int(n_samples))
+        idx, _total = self.ctx.basis_sample(circuit.U_full, ins, uniform, _threshold(), self._backend_id)
+        m, n = circuit.n_modes, sum(ins)
+        unrank = _lib.fock_unrank if self._backend_id == _lib.BACKEND_PERMANENT else _lib.slos_unrank
+        return {_state_cls(unrank(m, n, int(r)).tolist()): c for r, c in Counter(idx.tolist()).items()}
+
+
 class PermanentBackendMixin(_B200Base):
     """PermanentBackend on the GPU: batched Glynn/Gray-code permanents (permanent.py:30-163)."""
 
@@ -141,6 +164,8 @@ class PermanentBackendMixin(_B200Base):
 
 class SLOSBackendMixin(_B200Base):
     """SLOSBackend on the GPU: layer-by-layer state-vector evolution (slos.py:28-138)."""
+
+    _backend_id = _lib.BACKEND_SLOS
 
     @property
     def name(self) -> str:

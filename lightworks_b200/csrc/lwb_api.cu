@@ -15,6 +15,7 @@
 #include "k1x.h"
 #include "misc_kernels.cuh"
 #include "perm_kernels.cuh"
+#include "sample_kernels.cuh"
 #include "slos_kernels.cuh"
 #include "variants.h"
 
@@ -55,7 +56,7 @@ struct lwb_context {
     cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernel
     cudaEvent_t chunk_done[8] = {};
     uint64_t* d_bin = nullptr;
-    Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall;
+    Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall, bCdf, bTile, bUni, bIdx;
     uint64_t launches = 0;
     K1xState* k1x = nullptr;
     std::mutex mu;
@@ -162,7 +163,7 @@ int lwb_destroy(lwb_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (Buf* b : {&h->bU, &h->bIn, &h->bOut, &h->bRes, &h->bPart, &h->bTmp, &h->bLayerA, &h->bLayerB, &h->bProbs,
-                   &h->bMarg, &h->bFirst, &h->bSmall})
+                   &h->bMarg, &h->bFirst, &h->bSmall, &h->bCdf, &h->bTile, &h->bUni, &h->bIdx})
         if (b->p) cudaFree(b->p);
     k1x_destroy(h->k1x);
     if (h->d_bin) cudaFree(h->d_bin);
@@ -896,6 +897,101 @@ int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const 
     if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
                                (unsigned long long)cap);
     return 0;
+}
+
+}  // extern "C"
+
+// ---- on-device sampling (sampler.py:329-349) --------------------------------------------------------------
+// d_total (optional, device): receives cdf[S-1], the sum of the kept probabilities
+static int sample_dev(lwb_handle h, const double* d_probs, uint64_t S, double threshold, const double* d_uniform,
+                      uint64_t n_samples, uint64_t* d_index, double* d_total) {
+    if (S == 0) return fail(LWB_E_ARG, "empty distribution");
+    CU(cudaSetDevice(h->device));
+    const uint64_t n_tiles = (S + SCAN_TILE - 1) / SCAN_TILE;
+    if (n_tiles > 0x7fffffffull) return fail(LWB_E_LIMIT, "distribution too large");
+    CK(ensure(h, h->bCdf, S * 8));
+    CK(ensure(h, h->bTile, (2 * n_tiles + 1) * 8));
+    double* tile_sum = (double*)h->bTile.p;
+    double* tile_off = tile_sum + n_tiles;
+    double* cdf = (double*)h->bCdf.p;
+    scan_tile_sums_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(d_probs, S, threshold, tile_sum);
+    scan_tile_offsets_kernel<<<1, 1024, 0, h->stream>>>(tile_sum, n_tiles, tile_off);
+    scan_tile_cdf_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(d_probs, S, threshold, tile_off, cdf);
+    h->launches += 3;
+    if (n_samples > 0) {
+        const uint64_t blocks = (n_samples + 255) / 256;
+        if (blocks > 0x7fffffffull) return fail(LWB_E_LIMIT, "too many samples");
+        sample_search_kernel<<<(unsigned)blocks, 256, 0, h->stream>>>(cdf, S, d_uniform, n_samples, d_index);
+        h->launches++;
+    }
+    if (d_total) CU(cudaMemcpyAsync(d_total, cdf + (S - 1), 8, cudaMemcpyDeviceToDevice, h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// uniforms in, indices + total out around a device-resident distribution
+static int sample_roundtrip(lwb_handle h, const double* d_probs, uint64_t S, double threshold, const double* uniform,
+                            uint64_t n_samples, uint64_t* index, double* total) {
+    CK(ensure(h, h->bUni, (n_samples + 1) * 8));
+    CK(ensure(h, h->bIdx, (n_samples + 1) * 8));
+    if (n_samples) CU(cudaMemcpyAsync(h->bUni.p, uniform, n_samples * 8, cudaMemcpyHostToDevice, h->stream));
+    double* d_total = (double*)h->bUni.p + n_samples;
+    CK(sample_dev(h, d_probs, S, threshold, (const double*)h->bUni.p, n_samples, (uint64_t*)h->bIdx.p, d_total));
+    double tot = 0.0;
+    if (n_samples) CU(cudaMemcpyAsync(index, h->bIdx.p, n_samples * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (total) *total = tot;
+    if (!(tot > 0.0)) return fail(LWB_E_ARG, "no probability above the threshold: nothing to sample from");
+    return 0;
+}
+
+extern "C" {
+
+int lwb_sample_dev(lwb_handle h, const double* d_probs, uint64_t S, double threshold, const double* d_uniform,
+                   uint64_t n_samples, uint64_t* d_index, double* d_total) {
+    if (!h || !d_probs || (n_samples && (!d_uniform || !d_index))) return fail(LWB_E_ARG, "null argument");
+    return sample_dev(h, d_probs, S, threshold, d_uniform, n_samples, d_index, d_total);
+}
+
+int lwb_sample(lwb_handle h, const double* probs, uint64_t S, double threshold, const double* uniform,
+               uint64_t n_samples, uint64_t* index, double* total) {
+    if (!h || !probs || (n_samples && (!uniform || !index))) return fail(LWB_E_ARG, "null argument");
+    if (S == 0) return fail(LWB_E_ARG, "empty distribution");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bProbs, S * 8));
+    CU(cudaMemcpyAsync(h->bProbs.p, probs, S * 8, cudaMemcpyHostToDevice, h->stream));
+    return sample_roundtrip(h, (const double*)h->bProbs.p, S, threshold, uniform, n_samples, index, total);
+}
+
+int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
+                     const double* uniform, uint64_t n_samples, uint64_t* index, double* total) {
+    if (!h || !U || !in_state || (n_samples && (!uniform || !index))) return fail(LWB_E_ARG, "null argument");
+    if (backend != LWB_BACKEND_PERMANENT && backend != LWB_BACKEND_SLOS) return fail(LWB_E_ARG, "backend %d", backend);
+    std::lock_guard<std::mutex> lk(h->mu);
+    int n = 0;
+    CK(slos_check(m, in_state, &n));  // size limits shared by both backends
+    if (backend == LWB_BACKEND_PERMANENT && n > LWB_K1_MAX_N)
+        return fail(LWB_E_LIMIT, "permanent backend supports up to %d photons (got %d)", LWB_K1_MAX_N, n);
+    CU(cudaSetDevice(h->device));
+    const uint64_t S = binom(host_bin(), m + n - 1, n);
+    CK(ensure(h, h->bU, (size_t)m * m * 16));
+    CK(ensure(h, h->bProbs, S * 8));
+    CU(cudaMemcpyAsync(h->bU.p, U, (size_t)m * m * 16, cudaMemcpyHostToDevice, h->stream));
+    if (n == 0) {
+        const double one = 1.0;
+        CU(cudaMemcpyAsync(h->bProbs.p, &one, 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    } else if (backend == LWB_BACKEND_PERMANENT) {
+        CK(ensure(h, h->bIn, (size_t)m));
+        CU(cudaMemcpyAsync(h->bIn.p, in_state, (size_t)m, cudaMemcpyHostToDevice, h->stream));
+        CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, 1, nullptr, 0, S, n, LWB_C128, 1,
+                         (double*)h->bProbs.p));
+    } else {
+        CK(slos_run_dev(h, (const double*)h->bU.p, m, in_state, 1, 1, (double*)h->bProbs.p));
+    }
+    return sample_roundtrip(h, (const double*)h->bProbs.p, S, threshold, uniform, n_samples, index, total);
 }
 
 }  // extern "C"

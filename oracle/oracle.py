@@ -335,3 +335,33 @@ def slos_calculate(U, in_state):  # noqa: N803
     if n < 0:
         raise RuntimeError("oracle slos failed")
     return keys[:n], amps[:n]
+
+
+# ---- sampling ---------------------------------------------------------
+def sample_indices(probs, uniform, threshold: float = -1.0) -> np.ndarray:
+    """Positions drawn by `uniform` from the distribution `probs`: restates
+    SamplerRunner._gen_samples_from_dist (simulation/sampler.py:329-349),
+        probs /= sum(probs); rng.choice(range(len(probs)), p=probs, size=N),
+    through numpy's published algorithm for Generator.choice with p (numpy/random/_generator.pyx):
+        cdf = p.cumsum(); cdf /= cdf[-1]; idx = cdf.searchsorted(rng.random(N), side="right").
+    Entries with p <= threshold count as zero: the reference's distribution dict does not hold them
+    (permanent.py:151, slos.py:74) and a zero-width interval is never drawn.  Pinned against numpy itself
+    (tests/test_oracle_golden.py::test_sample_indices_is_numpy_choice)."""
+    p = np.asarray(probs, dtype=np.float64).copy()
+    p[~(p > threshold)] = 0.0
+    cdf = p.cumsum()
+    cdf /= cdf[-1]
+    return cdf.searchsorted(np.asarray(uniform, dtype=np.float64), side="right").astype(np.uint64)
+
+
+def sample_states(dist: dict, n_samples: int, seed=None) -> dict:
+    """_gen_samples_from_dist(dist, n_samples, seed, normalize=True) verbatim in behaviour (sampler.py:329-349):
+    {state: count} for a dict distribution, drawn with numpy's Generator exactly as the reference does."""
+    from collections import Counter
+
+    mapping = dict(enumerate(dist))
+    probs = np.array(list(dist.values()), dtype=float)
+    probs /= sum(probs)
+    rng = np.random.default_rng(seed)
+    samples = rng.choice(range(len(mapping)), p=probs, size=n_samples)
+    return {mapping[n]: c for n, c in Counter(samples).items()}

@@ -138,3 +138,19 @@ def test_reference_qubit_and_tomography_suites_run_on_b200():
                        cwd=ROOT, capture_output=True, text=True, timeout=1500)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
+
+
+@pytest.mark.parametrize("name", ["permanent", "slos"])
+def test_sample_outputs_equals_reference_sampler(lw, name):
+    """On-device sampling (lwb_basis_sample) against the unmodified Sampler task on the reference CPU backend with
+    the same seed: sampler.py:240-349 end to end."""
+    from lightworks.emulator import Backend
+
+    circ = lw.Unitary(lw.random_unitary(8, seed=5))
+    st = lw.State([1, 0, 1, 0, 1, 0, 1, 0])
+    task = lw.Sampler(circ, st, 5000, random_seed=21)
+    ref = dict(Backend(name + "_cpu").run(task))
+    got = Backend(name)._backend.sample_outputs(task._generate_task().circuit, st, 5000, seed=21)
+    assert sum(got.values()) == 5000
+    common = sum(min(got.get(k, 0), ref.get(k, 0)) for k in set(got) | set(ref))
+    assert common >= 5000 - 2

@@ -139,3 +139,23 @@ def test_mt_drivers_equal_serial():
     rng = np.random.default_rng(0)
     A = rng.normal(size=(17, 6, 6)) + 1j * rng.normal(size=(17, 6, 6))  # noqa: N806
     assert np.array_equal(O.perm_batch(A), O.perm_batch(A, threads=4))
+
+
+@pytest.mark.parametrize("S,n,seed", [(1, 10, 0), (7, 1000, 1), (4097, 20000, 2), (100003, 50000, 3)])
+def test_sample_indices_is_numpy_choice(S, n, seed):  # noqa: N803
+    """The sampling oracle against the reference's own sampler dependency: rng.choice (sampler.py:346-347)."""
+    rng = np.random.default_rng(100 + seed)
+    p = rng.random(S) ** 4
+    p[rng.random(S) < 0.2] = 0.0
+    if not p.any():
+        p[0] = 1.0
+    p /= p.sum()
+    ref = np.random.default_rng(seed).choice(range(S), p=p, size=n)
+    got = O.sample_indices(p, np.random.default_rng(seed).random(n))
+    assert np.array_equal(ref, got.astype(ref.dtype))
+    # the dict form the reference uses, with normalize=True
+    dist = {i: float(v) for i, v in enumerate(p) if v > 0}
+    counts = O.sample_states(dist, n, seed)
+    keys = np.array(list(dist))
+    ref2 = np.random.default_rng(seed).choice(range(len(dist)), p=np.array(list(dist.values())) / sum(dist.values()), size=n)
+    assert counts == {int(k): int(c) for k, c in zip(*np.unique(keys[ref2], return_counts=True))}
