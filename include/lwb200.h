@@ -148,6 +148,34 @@ int lwb_sample_dev(lwb_handle h, const double* d_probs, uint64_t S, double thres
 int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
                      const double* uniform, uint64_t n_samples, uint64_t* index, double* total);
 
+/* ---- dense distributions and their merge-convolution -------------------------------------------------
+ * pdist_calc / annotated_state_pdist_calc (simulation/probability_distribution.py:25-164): the output distribution
+ * of an imperfect source is a weighted sum, over the source's annotated inputs, of the CONVOLUTION of the
+ * distributions of the mutually distinguishable photon groups ("new_pdist[output.merge(result)] += p1 * p2",
+ * :150-158).  A distribution lives on the device as a dense float64 vector over the key space
+ *     K(n_modes, kmax) = occupation vectors of n_modes modes holding 0..kmax photons,
+ *     index(s) = sum_{j<k} C(n_modes+j-1, j) + fock_basis rank of s among the k-photon states (k = photons of s),
+ * addressed through an integer slot of the handle.
+ *   lwb_dist_from_circuit: {Permanent,SLOS}Backend.full_probability_distribution (permanent.py:116-163,
+ *       slos.py:43-80; threshold, loss-mode marginalisation, vacuum entry) straight into a slot (nothing returns
+ *       to the host);
+ *   lwb_dist_convolve: out = a (*) b, new slot over K(n_modes, kmax_a + kmax_b);
+ *   lwb_dist_axpy: acc += alpha * x (probability_distribution.py:160-164 / :62-69);
+ *   lwb_dist_sample: lwb_sample on a slot;  lwb_dist_download: the dense vector (size from lwb_dist_info). */
+int lwb_keyspace_size(int n_modes, int kmax, uint64_t* size);
+int lwb_keyspace_index(int n_modes, const uint8_t* state, uint64_t* index);
+int lwb_keyspace_state(int n_modes, int kmax, uint64_t index, uint8_t* state);
+int lwb_keyspace_states(int n_modes, int kmax, const uint64_t* indices, uint64_t count, uint8_t* states);
+int lwb_dist_create(lwb_handle h, int n_modes, int kmax, const double* dense_or_null, int* slot);
+int lwb_dist_from_circuit(lwb_handle h, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state,
+                          double threshold, int backend, int dtype, int* slot);
+int lwb_dist_convolve(lwb_handle h, int slot_a, int slot_b, int* slot_out);
+int lwb_dist_axpy(lwb_handle h, int slot_acc, double alpha, int slot_x);
+int lwb_dist_info(lwb_handle h, int slot, int* n_modes, int* kmax, uint64_t* size, void** device_ptr);
+int lwb_dist_download(lwb_handle h, int slot, double* dense);
+int lwb_dist_sample(lwb_handle h, int slot, const double* uniform, uint64_t n_samples, uint64_t* index, double* total);
+int lwb_dist_free(lwb_handle h, int slot);
+
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */
 int lwb_fp64_peak(lwb_handle h, double* flops_per_s);

@@ -12,6 +12,7 @@ from ._lib import (  # noqa: F401
     BackendError,
     Context,
     PhotonNumberError,
+    DeviceDistribution,
     default_context,
     fock_count,
     fock_rank,
@@ -28,8 +29,10 @@ from .backends import (  # noqa: E402, F401
     PermanentBackend,
     SLOSBackend,
     install,
+    set_convolve_on_gpu,
     uninstall,
 )
+from .convolution import DistributionAlgebra, pdist_calc  # noqa: E402, F401
 from .state import CompiledCircuitView, State  # noqa: E402, F401
 
 __version__ = "0.1.0"

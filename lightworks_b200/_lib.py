@@ -69,6 +69,18 @@ SIGNATURES = {
     "lwb_sample": (_i, [_vp, _vp, _u64, _dbl, _vp, _u64, _vp, _pdbl]),
     "lwb_sample_dev": (_i, [_vp, _vp, _u64, _dbl, _vp, _u64, _vp, _vp]),
     "lwb_basis_sample": (_i, [_vp, _i, _vp, _i, _vp, _dbl, _vp, _u64, _vp, _pdbl]),
+    "lwb_keyspace_size": (_i, [_i, _i, _pu64]),
+    "lwb_keyspace_index": (_i, [_i, _vp, _pu64]),
+    "lwb_keyspace_state": (_i, [_i, _i, _u64, _vp]),
+    "lwb_keyspace_states": (_i, [_i, _i, _vp, _u64, _vp]),
+    "lwb_dist_create": (_i, [_vp, _i, _i, _vp, _pi]),
+    "lwb_dist_from_circuit": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _i, _pi]),
+    "lwb_dist_convolve": (_i, [_vp, _i, _i, _pi]),
+    "lwb_dist_axpy": (_i, [_vp, _i, _dbl, _i]),
+    "lwb_dist_info": (_i, [_vp, _i, _pi, _pi, _pu64, C.POINTER(_vp)]),
+    "lwb_dist_download": (_i, [_vp, _i, _vp]),
+    "lwb_dist_sample": (_i, [_vp, _i, _vp, _u64, _vp, _pdbl]),
+    "lwb_dist_free": (_i, [_vp, _i]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
     "lwb_fp64_probe": (_i, [_vp, _i, _pdbl]),
 }
@@ -156,6 +168,80 @@ def slos_unrank(m: int, n: int, rank: int) -> np.ndarray:
     s = np.zeros(m, dtype=np.uint8)
     check(cdll().lwb_slos_unrank(m, n, rank, ptr(s)))
     return s
+
+
+def keyspace_size(n_modes: int, kmax: int) -> int:
+    """Number of occupation vectors of n_modes modes with 0..kmax photons (the dense distribution layout)."""
+    out = C.c_uint64(0)
+    check(cdll().lwb_keyspace_size(n_modes, kmax, C.byref(out)))
+    return int(out.value)
+
+
+def keyspace_index(state) -> int:
+    s = _u8(state)
+    out = C.c_uint64(0)
+    check(cdll().lwb_keyspace_index(len(s), ptr(s), C.byref(out)))
+    return int(out.value)
+
+
+def keyspace_state(n_modes: int, kmax: int, index: int) -> np.ndarray:
+    s = np.zeros(n_modes, dtype=np.uint8)
+    check(cdll().lwb_keyspace_state(n_modes, kmax, index, ptr(s)))
+    return s
+
+
+def keyspace_states(n_modes: int, kmax: int, indices) -> np.ndarray:
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    out = np.zeros((len(idx), n_modes), dtype=np.uint8)
+    check(cdll().lwb_keyspace_states(n_modes, kmax, ptr(idx), len(idx), ptr(out)))
+    return out
+
+
+class DeviceDistribution:
+    """A dense distribution over the key space K(n_modes, kmax) resident on the GPU (one slot of a Context).
+    `a @ b` is the merge-convolution of probability_distribution.py:150-158; freed with the object."""
+
+    def __init__(self, ctx: "Context", slot: int):
+        self.ctx, self.slot = ctx, slot
+        nm, km, sz = C.c_int(0), C.c_int(0), C.c_uint64(0)
+        check(cdll().lwb_dist_info(ctx.handle, slot, C.byref(nm), C.byref(km), C.byref(sz), None))
+        self.n_modes, self.kmax, self.size = nm.value, km.value, int(sz.value)
+
+    def __matmul__(self, other: "DeviceDistribution") -> "DeviceDistribution":
+        out = C.c_int(-1)
+        check(cdll().lwb_dist_convolve(self.ctx.handle, self.slot, other.slot, C.byref(out)))
+        return DeviceDistribution(self.ctx, out.value)
+
+    def add_scaled(self, alpha: float, x: "DeviceDistribution") -> None:
+        check(cdll().lwb_dist_axpy(self.ctx.handle, self.slot, float(alpha), x.slot))
+
+    def to_numpy(self) -> np.ndarray:
+        out = np.zeros(self.size, dtype=np.float64)
+        check(cdll().lwb_dist_download(self.ctx.handle, self.slot, ptr(out)))
+        return out
+
+    def sample(self, uniform):
+        uniform = np.ascontiguousarray(uniform, dtype=np.float64)
+        idx = np.zeros(len(uniform), dtype=np.uint64)
+        total = C.c_double(0)
+        check(cdll().lwb_dist_sample(self.ctx.handle, self.slot, ptr(uniform), len(uniform), ptr(idx), C.byref(total)))
+        return idx, float(total.value)
+
+    def device_ptr(self) -> int:
+        p = C.c_void_p(0)
+        check(cdll().lwb_dist_info(self.ctx.handle, self.slot, None, None, None, C.byref(p)))
+        return int(p.value)
+
+    def free(self):
+        if self.slot >= 0 and self.ctx.handle:
+            cdll().lwb_dist_free(self.ctx.handle, self.slot)
+        self.slot = -1
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
 
 
 # ---- device context ---------------------------------------------------------------------------------
@@ -346,8 +432,34 @@ def _slos_methods():
                                       len(uniform), ptr(idx), C.byref(total)))
         return idx, float(total.value)
 
+    def dist_zeros(self, n_modes, kmax):
+        out = C.c_int(-1)
+        check(cdll().lwb_dist_create(self._h, n_modes, kmax, None, C.byref(out)))
+        return DeviceDistribution(self, out.value)
+
+    def dist_from_dense(self, n_modes, kmax, dense):
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        if len(dense) != keyspace_size(n_modes, kmax):
+            raise ValueError("dense vector does not match the key space")
+        out = C.c_int(-1)
+        check(cdll().lwb_dist_create(self._h, n_modes, kmax, ptr(dense), C.byref(out)))
+        return DeviceDistribution(self, out.value)
+
+    def dist_from_circuit(self, U_full, n_modes, in_state, threshold=1e-9, backend=BACKEND_PERMANENT, dtype=LWB_C128):  # noqa: N803
+        """full_probability_distribution (permanent.py:116-163 / slos.py:43-80) into a device-resident dense
+        distribution over K(n_modes, photons of in_state)."""
+        U_full = np.ascontiguousarray(U_full, dtype=np.complex128)  # noqa: N806
+        s = _u8(in_state)
+        m_tot = U_full.shape[0]
+        if U_full.ndim != 2 or U_full.shape[1] != m_tot or len(s) != n_modes or n_modes > m_tot:
+            raise ValueError("unitary / state dimensions do not match")
+        out = C.c_int(-1)
+        check(cdll().lwb_dist_from_circuit(self._h, ptr(U_full), m_tot, n_modes, ptr(s), float(threshold), backend,
+                                           dtype, C.byref(out)))
+        return DeviceDistribution(self, out.value)
+
     for f in (slos_amplitudes, slos_basis_probs, slos_basis_probs_dev, slos_amplitudes_dev, pdist, sample, sample_dev,
-              basis_sample):
+              basis_sample, dist_zeros, dist_from_dense, dist_from_circuit):
         setattr(Context, f.__name__, f)
 
 

@@ -25,6 +25,16 @@ _DTYPES = {"complex128": _lib.LWB_C128, "complex64": _lib.LWB_C64, _lib.LWB_C128
 # Rebound to lightworks.State / settings by install(); module-level so the mixins stay import-light.
 _state_cls = State
 _settings = None
+_convolve_on_gpu = False
+
+
+def set_convolve_on_gpu(flag: bool) -> None:
+    """Opt in to combining the source statistics on the device: after install(), a Sampler on a B200 backend then
+    routes `pdist_calc` (simulation/probability_distribution.py:25-164, called at simulation/sampler.py:96) through
+    lightworks_b200.convolution.pdist_calc.  Off by default because the returned dict is in key-space order, not
+    in the reference's first-merged order (same distribution, different seeded samples)."""
+    global _convolve_on_gpu
+    _convolve_on_gpu = bool(flag)
 
 
 def _threshold() -> float:
@@ -343,10 +353,24 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
         run = _run
 
     import lightworks.emulator.backends as lw_backends_pkg
+    import lightworks.emulator.simulation.sampler as lw_sampler_mod
+
+    ref_pdist_calc = lw_sampler_mod.pdist_calc
+
+    def _pdist_calc(circuit, inputs, probability_func):
+        """simulation/sampler.py:96 calls this name; B200 backends may combine the inputs on the device."""
+        owner = getattr(probability_func, "__self__", None)
+        if _convolve_on_gpu and isinstance(owner, _B200Base):
+            from .convolution import pdist_calc as gpu_pdist_calc
+
+            return gpu_pdist_calc(circuit, inputs, owner).to_dict()
+        return ref_pdist_calc(circuit, inputs, probability_func)
+
+    lw_sampler_mod.pdist_calc = _pdist_calc
 
     _installed = {"old_map": LwBackend._backend_map, "classes": (B200PermanentBackend, B200SLOSBackend),
                   "Backend": LwBackend, "pkg": lw_backends_pkg, "patched": patch_names,
-                  "ref": (RefPermanent, RefSLOS)}
+                  "ref": (RefPermanent, RefSLOS), "sampler_mod": lw_sampler_mod, "ref_pdist_calc": ref_pdist_calc}
     if patch_names:
         lw_backends_pkg.PermanentBackend = B200PermanentBackend
         lw_backends_pkg.SLOSBackend = B200SLOSBackend
@@ -367,6 +391,7 @@ def uninstall():
     _installed["Backend"]._backend_map = _installed["old_map"]
     if _installed["patched"]:
         _installed["pkg"].PermanentBackend, _installed["pkg"].SLOSBackend = _installed["ref"]
+    _installed["sampler_mod"].pdist_calc = _installed["ref_pdist_calc"]
     _installed = None
     _state_cls = State
     _settings = None

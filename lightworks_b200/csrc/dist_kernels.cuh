@@ -1,0 +1,108 @@
+// dist_kernels.cuh -- dense output distributions on the device and their "merge-convolution"
+// (SURVEY.md section 8f rank 1).
+//
+// Replaces the nested dict loops of annotated_state_pdist_calc
+// (lightworks/emulator/simulation/probability_distribution.py:135-164):
+//     for output, p1 in pdist.items():
+//         for result, p2 in unique_results[d]:
+//             new_pdist[output.merge(result)] += p1 * p2          # State.merge = mode-wise sum of occupations
+// i.e. the distribution of the SUM of two independent occupation vectors (photons that carry different labels do
+// not interfere, so their output distributions convolve).
+//
+// Layout: a distribution over the measured modes is a dense float64 vector over the key space
+//     K(n_modes, kmax) = all occupation vectors of n_modes modes with 0..kmax photons,
+//     index(s) = off[k] + colex_rank(s),  k = photons of s,  off[k] = sum_{j<k} C(n_modes + j - 1, j),
+// (the photon-number blocks of lossy circuits side by side, each in the reference's fock_basis order), so
+// K(n_modes, k) is a prefix of K(n_modes, k') for k < k' and `acc += alpha * x` is a prefix axpy.
+//
+// convolve_kernel is the GATHER form: one thread per output state t walks every sub-multiset a of t (an odometer
+// over v_i in [0, s_i] for the distinct occupied modes), ranks a and t - a, and accumulates A[a] * B[t - a].  Same
+// number of products as the reference's double loop, but no atomics, a fixed summation order, and no State objects.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fock.cuh"
+
+namespace lwb {
+
+constexpr int DIST_THREADS = 256;
+
+struct ConvolveArgs {
+    const uint64_t* bin;
+    int n_modes;
+    int ka_min, ka_max;  // photon-number blocks of A that can be non-zero
+    int kb_min, kb_max;
+    const double* A;     // over K(n_modes, ka_max)
+    const double* B;     // over K(n_modes, kb_max)
+    double* out;         // over K(n_modes, ka_max + kb_max)
+    uint64_t size_out;
+    uint64_t off[LWB_MAX_PHOTONS + 2];  // off[k] for k = 0 .. ka_max + kb_max + 1
+};
+
+template <int KMAX>
+__global__ void __launch_bounds__(DIST_THREADS) convolve_kernel(ConvolveArgs a) {
+    const uint64_t o = (uint64_t)blockIdx.x * DIST_THREADS + threadIdx.x;
+    if (o >= a.size_out) return;
+    int kt = 0;
+    while (o >= a.off[kt + 1]) ++kt;
+    if (kt < a.ka_min + a.kb_min) { a.out[o] = 0.0; return; }
+    int dm[KMAX], s[KMAX], v[KMAX];
+    int d = 0;
+    {
+        int x[KMAX];
+        colex_unrank(a.bin, o - a.off[kt], kt, a.n_modes, x);
+        for (int i = 0; i < kt; ++i) {
+            if (i > 0 && x[i] == x[i - 1]) { s[d - 1] += 1; continue; }
+            dm[d] = x[i];
+            s[d] = 1;
+            v[d] = 0;
+            ++d;
+        }
+    }
+    double acc = 0.0;
+    int ka = 0;
+    for (;;) {
+        const int kb = kt - ka;
+        if (ka >= a.ka_min && ka <= a.ka_max && kb >= a.kb_min && kb <= a.kb_max) {
+            // colex ranks of a = {dm_i : v_i} and b = {dm_i : s_i - v_i}: sum over photons, ascending, of C(mode + i - 1, i)
+            uint64_t ra = 0, rb = 0;
+            int ia = 1, ib = 1;
+            for (int i = 0; i < d; ++i) {
+                for (int c = 0; c < v[i]; ++c, ++ia) ra += binom(a.bin, dm[i] + ia - 1, ia);
+                for (int c = v[i]; c < s[i]; ++c, ++ib) rb += binom(a.bin, dm[i] + ib - 1, ib);
+            }
+            acc += a.A[a.off[ka] + ra] * a.B[a.off[kb] + rb];
+        }
+        int i = 0;  // odometer
+        while (i < d && v[i] == s[i]) { ka -= v[i]; v[i] = 0; ++i; }
+        if (i == d) break;
+        v[i] += 1;
+        ka += 1;
+    }
+    a.out[o] = acc;
+}
+
+// acc[i] += alpha * x[i] over the (prefix) key space of x
+static __global__ void dist_axpy_kernel(double* __restrict__ acc, double alpha, const double* __restrict__ x, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) acc[i] += alpha * x[i];
+}
+
+// dst[i] = src[i] > threshold ? src[i] : 0   (strict, per full state: permanent.py:151, slos.py:74)
+static __global__ void dist_threshold_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, double threshold,
+                                                  uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const double p = src[i];
+        dst[i] = p > threshold ? p : 0.0;
+    }
+}
+
+// permanent.py:159-161: vacuum = 1 - sum when the marginalised entries sum to less than 1.  `sum` = tile_off[n_tiles]
+// of the scan over entries [1, size).
+static __global__ void dist_vacuum_kernel(double* dist, const double* sum) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) dist[0] = *sum < 1.0 ? 1.0 - *sum : 0.0;
+}
+
+}  // namespace lwb

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/lwb200.h"
+#include "dist_kernels.cuh"
 #include "fock.cuh"
 #include "k1x.h"
 #include "misc_kernels.cuh"
@@ -59,6 +60,12 @@ struct lwb_context {
     Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall, bCdf, bTile, bUni, bIdx;
     uint64_t launches = 0;
     K1xState* k1x = nullptr;
+    struct DistSlot {  // dense distribution over the key space K(n_modes, kmax), device resident
+        double* p = nullptr;
+        int n_modes = 0, kmin = 0, kmax = 0;
+        uint64_t size = 0;
+    };
+    std::vector<DistSlot> dists;
     std::mutex mu;
 };
 
@@ -166,6 +173,8 @@ int lwb_destroy(lwb_handle h) {
                    &h->bMarg, &h->bFirst, &h->bSmall, &h->bCdf, &h->bTile, &h->bUni, &h->bIdx})
         if (b->p) cudaFree(b->p);
     k1x_destroy(h->k1x);
+    for (auto& d : h->dists)
+        if (d.p) cudaFree(d.p);
     if (h->d_bin) cudaFree(h->d_bin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -992,6 +1001,262 @@ int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const ui
         CK(slos_run_dev(h, (const double*)h->bU.p, m, in_state, 1, 1, (double*)h->bProbs.p));
     }
     return sample_roundtrip(h, (const double*)h->bProbs.p, S, threshold, uniform, n_samples, index, total);
+}
+
+}  // extern "C"
+
+// ---- dense distributions and their merge-convolution (probability_distribution.py:25-164) -----------------
+static uint64_t keyspace_off(int n_modes, int k) {  // states with fewer than k photons
+    uint64_t o = 0;
+    for (int j = 0; j < k; ++j) o += binom(host_bin(), n_modes + j - 1, j);
+    return o;
+}
+static int keyspace_check(int n_modes, int kmax) {
+    if (n_modes < 1 || n_modes > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", n_modes, LWB_MAX_MODES);
+    if (kmax < 0 || kmax > LWB_MAX_PHOTONS) return fail(LWB_E_LIMIT, "photons n=%d outside [0,%d]", kmax, LWB_MAX_PHOTONS);
+    if (n_modes + kmax - 1 >= LWB_BIN_A) return fail(LWB_E_LIMIT, "m+n too large");
+    uint64_t o = 0;
+    for (int j = 0; j <= kmax; ++j) {
+        const uint64_t c = binom(host_bin(), n_modes + j - 1, j);
+        if (c == UINT64_MAX || o > (1ull << 40) - c) return fail(LWB_E_LIMIT, "key space too large");
+        o += c;
+    }
+    return 0;
+}
+static int new_slot(lwb_handle h, int n_modes, int kmin, int kmax, int* slot) {
+    CK(keyspace_check(n_modes, kmax));
+    lwb_context::DistSlot d;
+    d.n_modes = n_modes; d.kmin = kmin; d.kmax = kmax; d.size = keyspace_off(n_modes, kmax + 1);
+    cudaError_t e = cudaMalloc((void**)&d.p, d.size * 8);
+    if (e != cudaSuccess) return fail(LWB_E_NOMEM, "cudaMalloc(%llu): %s", (unsigned long long)(d.size * 8), cudaGetErrorString(e));
+    for (size_t i = 0; i < h->dists.size(); ++i)
+        if (!h->dists[i].p) { h->dists[i] = d; *slot = (int)i; return 0; }
+    h->dists.push_back(d);
+    *slot = (int)h->dists.size() - 1;
+    return 0;
+}
+static int get_slot(lwb_handle h, int slot, lwb_context::DistSlot** d) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    if (slot < 0 || slot >= (int)h->dists.size() || !h->dists[slot].p) return fail(LWB_E_ARG, "no distribution in slot %d", slot);
+    *d = &h->dists[slot];
+    return 0;
+}
+
+extern "C" {
+
+int lwb_keyspace_size(int n_modes, int kmax, uint64_t* size) {
+    if (!size) return fail(LWB_E_ARG, "null argument");
+    CK(keyspace_check(n_modes, kmax));
+    *size = keyspace_off(n_modes, kmax + 1);
+    return 0;
+}
+
+int lwb_keyspace_index(int n_modes, const uint8_t* state, uint64_t* index) {
+    if (!state || !index) return fail(LWB_E_ARG, "null argument");
+    const int k = photons_of(state, n_modes);
+    CK(keyspace_check(n_modes, k));
+    int x[LWB_MAX_PHOTONS + 1];
+    state_to_modes(state, n_modes, x);
+    *index = keyspace_off(n_modes, k) + colex_rank(host_bin(), x, k);
+    return 0;
+}
+
+int lwb_keyspace_state(int n_modes, int kmax, uint64_t index, uint8_t* state) {
+    if (!state) return fail(LWB_E_ARG, "null argument");
+    CK(keyspace_check(n_modes, kmax));
+    if (index >= keyspace_off(n_modes, kmax + 1)) return fail(LWB_E_ARG, "index outside the key space");
+    int k = 0;
+    while (index >= keyspace_off(n_modes, k + 1)) ++k;
+    int x[LWB_MAX_PHOTONS + 1];
+    colex_unrank(host_bin(), index - keyspace_off(n_modes, k), k, n_modes, x);
+    modes_to_state(x, k, n_modes, state);
+    return 0;
+}
+
+int lwb_keyspace_states(int n_modes, int kmax, const uint64_t* indices, uint64_t count, uint8_t* states) {
+    if (count && (!indices || !states)) return fail(LWB_E_ARG, "null argument");
+    CK(keyspace_check(n_modes, kmax));
+    uint64_t off[LWB_MAX_PHOTONS + 2];
+    for (int k = 0; k <= kmax + 1; ++k) off[k] = keyspace_off(n_modes, k);
+    for (uint64_t c = 0; c < count; ++c) {
+        const uint64_t index = indices[c];
+        if (index >= off[kmax + 1]) return fail(LWB_E_ARG, "index outside the key space");
+        int k = 0;
+        while (index >= off[k + 1]) ++k;
+        int x[LWB_MAX_PHOTONS + 1];
+        colex_unrank(host_bin(), index - off[k], k, n_modes, x);
+        modes_to_state(x, k, n_modes, states + c * (uint64_t)n_modes);
+    }
+    return 0;
+}
+
+int lwb_dist_create(lwb_handle h, int n_modes, int kmax, const double* dense, int* slot) {
+    if (!h || !slot) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CK(new_slot(h, n_modes, 0, kmax, slot));
+    auto& d = h->dists[*slot];
+    if (dense) CU(cudaMemcpyAsync(d.p, dense, d.size * 8, cudaMemcpyHostToDevice, h->stream));
+    else CU(cudaMemsetAsync(d.p, 0, d.size * 8, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_dist_free(lwb_handle h, int slot) {
+    lwb_context::DistSlot* d = nullptr;
+    CK(get_slot(h, slot, &d));
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(d->p));
+    *d = lwb_context::DistSlot();
+    return 0;
+}
+
+int lwb_dist_info(lwb_handle h, int slot, int* n_modes, int* kmax, uint64_t* size, void** device_ptr) {
+    lwb_context::DistSlot* d = nullptr;
+    CK(get_slot(h, slot, &d));
+    if (n_modes) *n_modes = d->n_modes;
+    if (kmax) *kmax = d->kmax;
+    if (size) *size = d->size;
+    if (device_ptr) *device_ptr = d->p;
+    return 0;
+}
+
+int lwb_dist_download(lwb_handle h, int slot, double* dense) {
+    lwb_context::DistSlot* d = nullptr;
+    CK(get_slot(h, slot, &d));
+    if (!dense) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(dense, d->p, d->size * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int lwb_dist_axpy(lwb_handle h, int slot_acc, double alpha, int slot_x) {
+    lwb_context::DistSlot *acc = nullptr, *x = nullptr;
+    CK(get_slot(h, slot_acc, &acc));
+    CK(get_slot(h, slot_x, &x));
+    if (acc->n_modes != x->n_modes || acc->kmax < x->kmax)
+        return fail(LWB_E_ARG, "accumulator (%d modes, <= %d photons) cannot hold (%d modes, <= %d photons)", acc->n_modes,
+                    acc->kmax, x->n_modes, x->kmax);
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    dist_axpy_kernel<<<(unsigned)((x->size + 255) / 256), 256, 0, h->stream>>>(acc->p, alpha, x->p, x->size);
+    h->launches++;
+    acc->kmin = std::min(acc->kmin, x->kmin);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lwb_dist_convolve(lwb_handle h, int slot_a, int slot_b, int* slot_out) {
+    lwb_context::DistSlot *pa = nullptr, *pb = nullptr;
+    CK(get_slot(h, slot_a, &pa));
+    CK(get_slot(h, slot_b, &pb));
+    if (!slot_out) return fail(LWB_E_ARG, "null argument");
+    if (pa->n_modes != pb->n_modes) return fail(LWB_E_ARG, "mode counts differ (%d, %d)", pa->n_modes, pb->n_modes);
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    const lwb_context::DistSlot A = *pa, B = *pb;  // new_slot may move the vector
+    CK(new_slot(h, A.n_modes, A.kmin + B.kmin, A.kmax + B.kmax, slot_out));
+    const auto& o = h->dists[*slot_out];
+    ConvolveArgs ca;
+    ca.bin = h->d_bin; ca.n_modes = A.n_modes; ca.ka_min = A.kmin; ca.ka_max = A.kmax; ca.kb_min = B.kmin; ca.kb_max = B.kmax;
+    ca.A = A.p; ca.B = B.p; ca.out = o.p; ca.size_out = o.size;
+    for (int k = 0; k <= o.kmax + 1; ++k) ca.off[k] = keyspace_off(A.n_modes, k);
+    CK(launch_kmax(h, o.kmax, o.size, 0, ca, convolve_kernel<4>, convolve_kernel<8>, convolve_kernel<12>, convolve_kernel<16>,
+                   convolve_kernel<24>, convolve_kernel<40>));
+    return 0;
+}
+
+int lwb_dist_sample(lwb_handle h, int slot, const double* uniform, uint64_t n_samples, uint64_t* index, double* total) {
+    lwb_context::DistSlot* d = nullptr;
+    CK(get_slot(h, slot, &d));
+    if (n_samples && (!uniform || !index)) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CU(cudaSetDevice(h->device));
+    return sample_roundtrip(h, d->p, d->size, -1.0, uniform, n_samples, index, total);
+}
+
+int lwb_dist_from_circuit(lwb_handle h, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state,
+                          double threshold, int backend, int dtype, int* slot) {
+    if (!h || !U_full || !in_state || !slot) return fail(LWB_E_ARG, "null argument");
+    if (backend != LWB_BACKEND_PERMANENT && backend != LWB_BACKEND_SLOS) return fail(LWB_E_ARG, "backend %d", backend);
+    if (n_modes < 1 || n_modes > m_tot) return fail(LWB_E_ARG, "n_modes=%d outside [1,%d]", n_modes, m_tot);
+    if (m_tot > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m_tot, LWB_MAX_MODES);
+    std::lock_guard<std::mutex> lk(h->mu);
+    const uint64_t* hb = host_bin();
+    const int loss = m_tot - n_modes;
+    int n = 0;
+    for (int i = 0; i < n_modes; ++i) n += in_state[i];
+    CK(check_mn(m_tot, n));
+    if (backend == LWB_BACKEND_PERMANENT && n > LWB_K1_MAX_N)
+        return fail(LWB_E_LIMIT, "permanent backend supports up to %d photons (got %d)", LWB_K1_MAX_N, n);
+    CU(cudaSetDevice(h->device));
+    CK(new_slot(h, n_modes, loss ? 0 : n, n, slot));
+    const auto d = h->dists[*slot];
+    CU(cudaMemsetAsync(d.p, 0, d.size * 8, h->stream));
+    if (n == 0) {  // permanent.py:137-138, slos.py:64-65
+        const double one = 1.0;
+        CU(cudaMemcpyAsync(d.p, &one, 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    uint8_t full_in[LWB_MAX_MODES];
+    memset(full_in, 0, sizeof full_in);
+    memcpy(full_in, in_state, (size_t)n_modes);  // permanent.py:142-143, slos.py:69-70
+    const uint64_t S = binom(hb, m_tot + n - 1, n);
+    CK(ensure(h, h->bU, (size_t)m_tot * m_tot * 16));
+    CK(ensure(h, h->bProbs, S * 8));
+    CU(cudaMemcpyAsync(h->bU.p, U_full, (size_t)m_tot * m_tot * 16, cudaMemcpyHostToDevice, h->stream));
+    if (backend == LWB_BACKEND_PERMANENT) {
+        CK(ensure(h, h->bIn, (size_t)m_tot));
+        CU(cudaMemcpyAsync(h->bIn.p, full_in, (size_t)m_tot, cudaMemcpyHostToDevice, h->stream));
+        CK(launch_states(h, (const double*)h->bU.p, m_tot, (const uint8_t*)h->bIn.p, 1, nullptr, 0, S, n, dtype, 1,
+                         (double*)h->bProbs.p));
+    } else {
+        CK(slos_run_dev(h, (const double*)h->bU.p, m_tot, full_in, 0, 1, (double*)h->bProbs.p));  // fock_basis order
+    }
+    if (loss == 0) {
+        dist_threshold_copy_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(d.p + keyspace_off(n_modes, n),
+                                                                                       (const double*)h->bProbs.p, threshold, S);
+        h->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(h->stream));  // full_in / U_full are the caller's
+        return 0;
+    }
+    // loss modes: marginalise straight into the key space (the marginal table IS the key-space layout)
+    const int k_min = backend == LWB_BACKEND_PERMANENT ? 1 : 0;  // permanent.py:148-149 skips zero-real-photon states
+    uint64_t key_off[LWB_MAX_PHOTONS + 3];
+    uint64_t nk = 0;
+    for (int kk = 0; kk <= n + 1; ++kk) {
+        key_off[kk] = nk;
+        if (kk >= k_min && kk <= n) nk += binom(hb, n_modes + kk - 1, kk);
+    }
+    CK(ensure(h, h->bFirst, nk * 8));
+    CK(ensure(h, h->bSmall, 4096));
+    CU(cudaMemcpyAsync((char*)h->bSmall.p + 2048, key_off, sizeof(uint64_t) * (size_t)(n + 2), cudaMemcpyHostToDevice, h->stream));
+    double* marg = d.p + (k_min ? 1 : 0);
+    MargArgs ma;
+    ma.bin = h->d_bin; ma.m_tot = m_tot; ma.n_modes = n_modes; ma.n = n; ma.k_min = k_min;
+    ma.key_off = (const uint64_t*)((char*)h->bSmall.p + 2048); ma.n_keys = nk; ma.probs = (const double*)h->bProbs.p;
+    ma.threshold = threshold; ma.order = 0; ma.marg = marg; ma.first_pos = (uint64_t*)h->bFirst.p;
+    CK(launch_kmax(h, n, nk, 0, ma, marginalise_kernel<4>, marginalise_kernel<8>, marginalise_kernel<12>,
+                   marginalise_kernel<16>, marginalise_kernel<24>, marginalise_kernel<40>));
+    if (backend == LWB_BACKEND_PERMANENT) {  // permanent.py:159-161: vacuum = 1 - sum if sum < 1
+        const uint64_t n_tiles = (nk + SCAN_TILE - 1) / SCAN_TILE;
+        CK(ensure(h, h->bTile, (2 * n_tiles + 1) * 8));
+        double* tile_sum = (double*)h->bTile.p;
+        double* tile_off = tile_sum + n_tiles;
+        scan_tile_sums_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(marg, nk, -1.0, tile_sum);
+        scan_tile_offsets_kernel<<<1, 1024, 0, h->stream>>>(tile_sum, n_tiles, tile_off);
+        dist_vacuum_kernel<<<1, 32, 0, h->stream>>>(d.p, tile_off + n_tiles);
+        h->launches += 3;
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 }  // extern "C"

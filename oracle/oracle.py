@@ -365,3 +365,81 @@ def sample_states(dist: dict, n_samples: int, seed=None) -> dict:
     rng = np.random.default_rng(seed)
     samples = rng.choice(range(len(mapping)), p=probs, size=n_samples)
     return {mapping[n]: c for n, c in Counter(samples).items()}
+
+
+# ---- source-statistics combination -------------------------------------
+def py_pdist_calc(circuit, inputs: dict, probability_func) -> dict:
+    """pdist_calc (simulation/probability_distribution.py:25-73) for State inputs, with tuples for states.
+    `circuit` needs n_modes and loss_modes; probability_func(circuit, state_tuple) -> dict[tuple, float]."""
+    pdist: dict = {}
+    for istate, prob in inputs.items():                      # :58
+        sub_dist = probability_func(circuit, istate)         # :60
+        if not pdist:                                        # :61-65
+            pdist = dict(sub_dist) if prob == 1 else {s: p * prob for s, p in sub_dist.items()}
+        else:                                                # :66-71
+            for s, p in sub_dist.items():
+                if s in pdist:
+                    pdist[s] += p * prob
+                else:
+                    pdist[s] = p * prob
+    total_prob = sum(pdist.values())                         # :73
+    if total_prob < 1 and circuit.loss_modes > 0:            # :74-75
+        pdist[tuple([0] * circuit.n_modes)] = 1 - total_prob
+    return pdist
+
+
+def py_annotated_pdist_calc(circuit, inputs: dict, probability_func) -> dict:
+    """annotated_state_pdist_calc (simulation/probability_distribution.py:78-164).  Annotated states are tuples
+    of per-mode label tuples; State.merge (sdk/state/state.py) is the mode-wise sum of occupations."""
+    n_modes = circuit.n_modes
+    unique_inputs: list = []
+    input_combinations: dict = {}
+    for state in inputs:                                     # :105-121
+        all_labels = [lab for mode in state for lab in mode]
+        if all_labels:
+            results = {lab: [0] * n_modes for lab in all_labels}
+            for i, mode in enumerate(state):
+                for m in mode:
+                    results[m][i] += 1
+            states = [tuple(s) for s in results.values()]
+        else:
+            states = [tuple([0] * n_modes)]
+        for s in states:
+            if s not in unique_inputs:
+                unique_inputs.append(s)
+        input_combinations[state] = states
+    unique_results = {s[:n_modes]: list(probability_func(circuit, s).items()) for s in unique_inputs}  # :124-133
+    stats_dict: dict = {}
+    for istate, combination in input_combinations.items():   # :137
+        pdist: dict = {}
+        for d in combination:                                # :140
+            if not pdist:
+                pdist = dict(unique_results[d])
+            else:
+                new_pdist: dict = {}
+                for output, p1 in pdist.items():             # :147-156
+                    for result, p2 in unique_results[d]:
+                        new_state = tuple(a + b for a, b in zip(output, result))
+                        if new_state not in new_pdist:
+                            new_pdist[new_state] = p1 * p2
+                        else:
+                            new_pdist[new_state] += p1 * p2
+                pdist = new_pdist
+        ip = inputs[istate]                                  # :159-164
+        for ostate, op in pdist.items():
+            if ostate not in stats_dict:
+                stats_dict[ostate] = ip * op
+            else:
+                stats_dict[ostate] += ip * op
+    return stats_dict
+
+
+def pdist_func(backend: str = "permanent", threshold: float = 1e-9):
+    """probability_func for the two restatements above, from the oracle's own full distributions."""
+    fn = pdist_permanent if backend == "permanent" else pdist_slos
+
+    def f(circuit, state):
+        keys, vals = fn(circuit.U_full, circuit.n_modes, list(state)[: circuit.n_modes], threshold)
+        return {tuple(int(v) for v in k): float(p) for k, p in zip(keys, vals)}
+
+    return f

@@ -154,3 +154,32 @@ def test_sample_outputs_equals_reference_sampler(lw, name):
     assert sum(got.values()) == 5000
     common = sum(min(got.get(k, 0), ref.get(k, 0)) for k in set(got) | set(ref))
     assert common >= 5000 - 2
+
+
+@pytest.mark.parametrize("name", ["permanent", "slos"])
+def test_imperfect_source_combined_on_device(lw, name):
+    """Opt-in device path for pdist_calc (probability_distribution.py:25-164): an unmodified Sampler with an
+    imperfect source on a lossy circuit, distribution compared entry by entry with the reference CPU backend."""
+    import lightworks_b200
+    from lightworks import emulator
+    from lightworks.emulator import Backend
+
+    circ = lw.PhotonicCircuit(5)
+    for i, mode in enumerate([0, 2, 1, 3, 0, 2]):
+        circ.bs(mode, reflectivity=0.3 + 0.1 * i, loss=0.05 * (i % 3))
+        circ.ps(mode + 1, 0.2 * i)
+    src = emulator.Source(purity=0.95, brightness=0.85, indistinguishability=0.9)
+    mk = lambda: lw.Sampler(circ, lw.State([1, 0, 1, 1, 0]), 2000, source=src, random_seed=3)  # noqa: E731
+    t1, t2 = mk(), mk()
+    lightworks_b200.set_convolve_on_gpu(True)
+    try:
+        r1 = Backend(name).run(t1)
+    finally:
+        lightworks_b200.set_convolve_on_gpu(False)
+    Backend(name + "_cpu").run(t2)
+    d1, d2 = dict(t1.probability_distribution), dict(t2.probability_distribution)
+    assert set(d1) == set(d2)
+    vac = lw.State([0] * 5)
+    for k, v in d2.items():
+        assert d1[k] == pytest.approx(v, rel=1e-9, abs=1e-12 if k == vac else 1e-16)
+    assert sum(dict(r1).values()) == 2000

@@ -159,3 +159,33 @@ def test_sample_indices_is_numpy_choice(S, n, seed):  # noqa: N803
     keys = np.array(list(dist))
     ref2 = np.random.default_rng(seed).choice(range(len(dist)), p=np.array(list(dist.values())) / sum(dist.values()), size=n)
     assert counts == {int(k): int(c) for k, c in zip(*np.unique(keys[ref2], return_counts=True))}
+
+
+def _convolve_records():
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_convolve.json")) as f:
+        return json.load(f)["records"]
+
+
+class _Circ:
+    def __init__(self, r):
+        self.U_full = np.array(r["U_re"]) + 1j * np.array(r["U_im"])
+        self.n_modes, self.loss_modes = r["n_modes"], r["loss_modes"]
+
+
+@pytest.mark.parametrize("r", _convolve_records(), ids=lambda r: f"{r['scenario'][:40]}[{r['backend']}]")
+def test_pdist_calc_restatement_matches_reference(r):
+    """oracle.py_pdist_calc / py_annotated_pdist_calc (probability_distribution.py:25-164) on the inputs the
+    reference's Source produced, against the distribution the unmodified reference returned: same states in the
+    same dict order, probabilities to 1e-12."""
+    circ = _Circ(r)
+    if r["annotated"]:
+        inputs = {tuple(tuple(mode) for mode in s): p for s, p in r["inputs"]}
+        got = O.py_annotated_pdist_calc(circ, inputs, O.pdist_func(r["backend"]))
+    else:
+        inputs = {tuple(s): p for s, p in r["inputs"]}
+        got = O.py_pdist_calc(circ, inputs, O.pdist_func(r["backend"]))
+    assert [list(k) for k in got] == r["keys"]
+    assert rel_close(list(got.values()), r["vals"], 1e-12, 1e-18)
