@@ -269,7 +269,13 @@ def main() -> int:  # noqa: PLR0915
     ins = np.array([1] * N_PH + [0] * (M - N_PH), dtype=np.uint8)
     S = lb.fock_count(M, N_PH)  # noqa: N806
     # contiguous rank-range shards; boundaries equalise the WORK of the multiplicity-aware walk (early ranks bunch more)
-    shard_ranges = sharding.work_balanced_ranges(M, N_PH, world)
+    # (exact cumulative-work bisection on the host, lightworks_b200/sharding.py)
+    # Pieces of decreasing work: the all-gather of a piece overlaps the kernels of the next one, so only the small last
+    # piece's exchange is exposed (8 GPUs: 1 piece 15.2 ms, 2 equal 14.2, 4 equal 14.4 per step).
+    fractions = [float(x) for x in os.environ.get("LWB_BENCH_PIECES", "0.6,0.3,0.1").split(",")] if world > 1 else [1.0]
+    SUB = len(fractions)  # noqa: N806
+    pieces = sharding.work_balanced_ranges(M, N_PH, world, fractions)
+    shard_ranges = [(pieces[r][0][0], pieces[r][-1][1]) for r in range(world)]
     r0, r1 = shard_ranges[rank]
     cnt = r1 - r0
 
@@ -282,8 +288,6 @@ def main() -> int:  # noqa: PLR0915
     # piece j+1.  Pieces have unequal lengths across ranks (equal work), so every rank writes its piece at the head of
     # a max-length slot and ONE ncclAllGather per piece moves the slots; the distribution on every rank is the ragged
     # view  d_full[j].view(world, slot_j)[r, :len(piece j of rank r)]  (padding stays zero).
-    SUB = 4 if world > 1 else 1  # noqa: N806
-    pieces = [[(a + (b - a) * j // SUB, a + (b - a) * (j + 1) // SUB) for j in range(SUB)] for a, b in shard_ranges]
     slot_len = [max(pieces[r][j][1] - pieces[r][j][0] for r in range(world)) for j in range(SUB)]
     with torch.cuda.stream(stream):
         d_U = torch.from_numpy(U).cuda()  # noqa: N806  resident inputs for the device-timed region
@@ -362,6 +366,24 @@ def main() -> int:  # noqa: PLR0915
     l0 = ctx.launch_count()
     dev_ms, dev_wall, clocks = timed(device_step, args.steps, sampler)
     launches = ctx.launch_count() - l0
+    per_rank_ms = None
+    if world > 1:
+        # balance diagnostic: every rank's own shard kernels WITHOUT the collectives (3 repetitions, best)
+        best = 1e30
+        with torch.cuda.stream(stream):
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for j in range(SUB):
+                    a, b = pieces[rank][j]
+                    ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, a, b - a, d_slot[j])
+                e1.record(stream)
+                e1.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+        t_all = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t_all[rank] = best
+        dist.all_reduce(t_all)
+        per_rank_ms = [round(float(v), 3) for v in t_all]
     dev_ms = max_over_ranks(dev_ms)
     total_sum = float(d_probs.sum()) if world == 1 else float(d_sum)
     if world > 1:
@@ -452,6 +474,8 @@ def main() -> int:  # noqa: PLR0915
                 "api": "lwb_perm_basis_probs (host buffers, pinned) via lightworks_b200.Context.perm_basis_probs"},
         "gpu_launches": int(launches), "clocks": clocks, "wall_ms_timed_region": dev_wall,
     }
+    if per_rank_ms is not None:
+        line["per_rank_compute_ms"] = per_rank_ms  # shard kernels only, no collectives
 
     if world > 1 and not args.no_extras:
         # C5: one 28 x 28 permanent of the 60-mode Haar unitary (seed 5), Gray-code space sliced over the ranks,

@@ -47,30 +47,116 @@ def _average_terms(m: int, n: int) -> float:
     return work / tot
 
 
-def work_balanced_ranges(m: int, n: int, world: int) -> list[tuple[int, int]]:
-    """Contiguous rank ranges of fock_basis(m, n) with (approximately) equal WORK for the multiplicity-aware
-    permanent walk.  In the reference order the states whose highest occupied mode is <= v are the rank prefix
-    [0, C(v+n, n)) and bunch more (fewer terms) than later ones; the cumulative work at those m breakpoints is
-    exact (combinatorics over multiplicity patterns) and interpolated linearly in between."""
+def _colex_unrank(rank: int, n: int) -> list[int]:
+    """Ascending mode list of the state at `rank` of fock_basis(m, n) (csrc/fock.cuh: rank = sum C(x_i + i - 1, i))."""
+    from math import comb
+
+    x = [0] * n
+    for i in range(n, 0, -1):
+        y = i - 1
+        while comb(y + 1, i) <= rank:
+            y += 1
+        rank -= comb(y, i)
+        x[i - 1] = y - i + 1
+    return x
+
+
+def _free_work(i: int, v: int) -> tuple[int, int]:
+    """Over all ways to put i photons into v modes: (sum of prod(s_j + 1), the same sum restricted to states whose
+    occupations are all even).  Generating functions (1 - z)^(-2v) and ((1 + z^2) / (1 - z^2)^2)^v."""
+    from math import comb
+
+    if v == 0:
+        return (1, 1) if i == 0 else (0, 0)
+    total = comb(i + 2 * v - 1, i)
+    even = 0
+    if i % 2 == 0:
+        h = i // 2
+        even = sum(comb(v, a) * comb(h - a + 2 * v - 1, 2 * v - 1) for a in range(min(v, h) + 1))
+    return total, even
+
+
+def cumulative_work(m: int, n: int, rank: int, overhead: float = 0.0) -> float:
+    """Exact work of the multiplicity-aware walk (csrc/k1x.h) over the rank prefix [0, rank) of fock_basis(m, n):
+    sum of terms(state) = prod(s_j + 1), halved when some occupation is odd, plus `overhead` term-equivalents per
+    state (unranking and prologue).  The states below `rank` split, by the highest photon in which they differ from
+    state(rank), into n blocks "photons above position i fixed, i photons free in the modes below y_i"; fixed and
+    free photons occupy disjoint modes, so the block sums factorise (closed forms in _free_work)."""
+    from math import comb
+
+    total_states = comb(m + n - 1, n)
+    if rank <= 0:
+        return 0.0
+    if rank >= total_states:
+        a, e = _free_work(n, m)
+        return (e + (a - e) // 2) + overhead * total_states
+    y = _colex_unrank(rank, n)
+    work = 0
+    for i in range(n, 0, -1):  # states with x_j = y_j for j > i and x_i < y_i
+        v = y[i - 1]           # free photons live in modes 0 .. v-1
+        if v == 0:
+            continue
+        fixed = y[i:]
+        f, odd = 1, False
+        for mode in set(fixed):
+            c = fixed.count(mode)
+            f *= c + 1
+            odd |= c % 2 == 1
+        a, e = _free_work(i, v)
+        work += f * a // 2 if odd else f * (e + (a - e) // 2)
+    return work + overhead * rank
+
+
+# per-state cost of classification, unranking and block prologue in units of one Glynn term: fitted to the per-rank
+# kernel times of the 8-GPU C3 run on B200 (ranks holding more, cheaper states ran longer with a smaller constant)
+STATE_OVERHEAD_TERMS = 63.0
+
+
+def work_cuts(m: int, n: int, fractions: list[float]) -> list[int]:
+    """Ranks of fock_basis(m, n) at which the cumulative work of the multiplicity-aware permanent walk reaches the
+    given fractions of the total (ascending, in [0, 1]); bisection on the exact cumulative work function (host
+    integer arithmetic, no device needed).  Below n = 7 the expanded-row kernel runs: uniform cost per state."""
     from math import comb
 
     total = comb(m + n - 1, n)
-    if world == 1 or n < 7:  # below n = 7 the expanded-row kernel is used: uniform cost per state
-        return [rank_range(total, r, world) for r in range(world)]
-    pts = [(0, 0.0)]
-    for v in range(m):
-        r = comb(v + n, n)
-        pts.append((r, _average_terms(v + 1, n) * r))
-    w_total = pts[-1][1]
-    cuts = [0]
-    for k in range(1, world):
-        target = w_total * k / world
-        for (r0, w0), (r1, w1) in zip(pts, pts[1:]):
-            if w0 <= target <= w1:
-                cuts.append(int(r0 + (r1 - r0) * (target - w0) / (w1 - w0)) if w1 > w0 else r0)
-                break
-    cuts.append(total)
-    return [(cuts[i], cuts[i + 1]) for i in range(world)]
+    if n < 7:
+        return [min(total, max(0, int(round(total * f)))) for f in fractions]
+    w_total = cumulative_work(m, n, total, STATE_OVERHEAD_TERMS)
+    cuts = []
+    for f in fractions:
+        if f <= 0:
+            cuts.append(0)
+            continue
+        if f >= 1:
+            cuts.append(total)
+            continue
+        target = w_total * f
+        lo, hi = (cuts[-1] if cuts else 0), total
+        while lo < hi:
+            mid = (lo + hi) // 2
+            if cumulative_work(m, n, mid, STATE_OVERHEAD_TERMS) < target:
+                lo = mid + 1
+            else:
+                hi = mid
+        cuts.append(lo)
+    return cuts
+
+
+def work_balanced_ranges(m: int, n: int, world: int, pieces: list[float] | None = None):
+    """Contiguous rank ranges of fock_basis(m, n) with equal WORK per rank: bunched states (early ranks) need fewer
+    terms, so equal-count shards would be up to ~1.3x out of balance.  With `pieces` (fractions of a shard summing
+    to 1, e.g. [0.6, 0.3, 0.1]) every shard is returned as a list of sub-ranges holding those work fractions, for
+    pipelines that exchange piece j while computing piece j+1."""
+    if pieces is None:
+        cuts = work_cuts(m, n, [k / world for k in range(world + 1)])
+        return [(cuts[i], cuts[i + 1]) for i in range(world)]
+    acc = [0.0]
+    for p in pieces:
+        acc.append(acc[-1] + p)
+    fr = [(r + a / acc[-1]) / world for r in range(world) for a in acc[:-1]] + [1.0]
+    cuts = work_cuts(m, n, fr)
+    k = len(pieces)
+    return [[(cuts[r * k + j], cuts[r * k + j + 1]) for j in range(k)] for r in range(world)]
 
 
 def allgather_shards(local, total: int, rank: int, world: int, group=None):

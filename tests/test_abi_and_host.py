@@ -132,3 +132,30 @@ def test_multiplicity_plan_host():
             assert p["abs_coef_sum"] == 2**n / p["factor"]
     with pytest.raises(ValueError):
         _lib.multiplicity_plan(17)
+
+
+def test_cumulative_work_is_exact_and_cuts_balance():
+    """sharding.cumulative_work against a brute-force sum over fock_basis (terms of the multiplicity-aware walk,
+    csrc/k1x.h), and the bisection cuts of work_balanced_ranges."""
+    from lightworks_b200 import sharding
+
+    for m, n in [(3, 2), (4, 3), (5, 4), (6, 5), (4, 6), (7, 3)]:
+        cum = [0]
+        for s in O.py_fock_basis(m, n):
+            occ = [v for v in s if v > 0]
+            t = int(np.prod([v + 1 for v in occ]))
+            if any(v % 2 for v in occ):
+                t //= 2
+            cum.append(cum[-1] + t)
+        for r in range(len(cum)):
+            assert sharding.cumulative_work(m, n, r) == cum[r]
+    # the walk's own plan (lwb_multiplicity_plan) agrees with the closed form of the total
+    m, n = 24, 10
+    total = lb.fock_count(m, n)
+    assert sharding.cumulative_work(m, n, total) / total == pytest.approx(sharding._average_terms(m, n), rel=1e-12)
+    for world in (2, 8, 16):
+        ranges = sharding.work_balanced_ranges(m, n, world)
+        assert ranges[0][0] == 0 and ranges[-1][1] == total and all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        c0 = sharding.STATE_OVERHEAD_TERMS
+        w = [sharding.cumulative_work(m, n, b, c0) - sharding.cumulative_work(m, n, a, c0) for a, b in ranges]
+        assert max(w) / (sum(w) / world) < 1.0001
