@@ -546,6 +546,11 @@ def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
     out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms,
                       "roofline": {"bound": "hbm", "achieved": slos_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes},
+                      "gather_traffic": {"bytes": 16 * M * sum(comb(M + k - 2, k - 1) for k in range(1, N_PH + 1)),
+                                         "achieved_gbs": 16 * M * sum(comb(M + k - 2, k - 1) for k in range(1, N_PH + 1)) / (ms * 1e-3) / 1e9,
+                                         "note": "every (child, occupied mode) edge of a layer reads a distinct parent "
+                                                 "amplitude: m*S(m,k-1) 16-byte gathers per layer through L1/L2; the DRAM "
+                                                 "figure above assumes each parent is fetched once"},
                       "note": "SLOS backend, same distribution in SLOS dict order, all 10 layers"}
     # on-device sampling of the same distribution: CDF build + search, device-resident, and the
     # whole Sampler chain through the host API (U in, 10^6 variates in, 10^6 drawn ranks out)

@@ -15,9 +15,10 @@
 // (the photon-number blocks of lossy circuits side by side, each in the reference's fock_basis order), so
 // K(n_modes, k) is a prefix of K(n_modes, k') for k < k' and `acc += alpha * x` is a prefix axpy.
 //
-// convolve_kernel is the GATHER form: one thread per output state t walks every sub-multiset a of t (an odometer
-// over v_i in [0, s_i] for the distinct occupied modes), ranks a and t - a, and accumulates A[a] * B[t - a].  Same
-// number of products as the reference's double loop, but no atomics, a fixed summation order, and no State objects.
+// convolve_kernel is the GATHER form: one thread per output state t walks the sub-multisets a of t that can be
+// non-zero in A (by photon number; the smaller part is enumerated as index combinations of the sorted photon list),
+// ranks a and t - a, and accumulates A[a] * B[t - a].  Same products as the reference's double loop, but no atomics,
+// a fixed summation order, and no State objects.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -46,39 +47,39 @@ __global__ void __launch_bounds__(DIST_THREADS) convolve_kernel(ConvolveArgs a) 
     if (o >= a.size_out) return;
     int kt = 0;
     while (o >= a.off[kt + 1]) ++kt;
-    if (kt < a.ka_min + a.kb_min) { a.out[o] = 0.0; return; }
-    int dm[KMAX], s[KMAX], v[KMAX];
-    int d = 0;
-    {
-        int x[KMAX];
-        colex_unrank(a.bin, o - a.off[kt], kt, a.n_modes, x);
-        for (int i = 0; i < kt; ++i) {
-            if (i > 0 && x[i] == x[i - 1]) { s[d - 1] += 1; continue; }
-            dm[d] = x[i];
-            s[d] = 1;
-            v[d] = 0;
-            ++d;
-        }
-    }
+    const int ka_lo = max(a.ka_min, kt - a.kb_max), ka_hi = min(a.ka_max, kt - a.kb_min);
+    if (ka_lo > ka_hi) { a.out[o] = 0.0; return; }
+    int x[KMAX], c[KMAX];
+    colex_unrank(a.bin, o - a.off[kt], kt, a.n_modes, x);
     double acc = 0.0;
-    int ka = 0;
-    for (;;) {
+    for (int ka = ka_lo; ka <= ka_hi; ++ka) {
+        // sub-multisets of t with ka photons <-> index combinations c_0 < ... < c_{q-1} of the sorted photon list that
+        // take the copies of a mode from the left ("canonical"); the smaller of the two parts is enumerated
         const int kb = kt - ka;
-        if (ka >= a.ka_min && ka <= a.ka_max && kb >= a.kb_min && kb <= a.kb_max) {
-            // colex ranks of a = {dm_i : v_i} and b = {dm_i : s_i - v_i}: sum over photons, ascending, of C(mode + i - 1, i)
-            uint64_t ra = 0, rb = 0;
-            int ia = 1, ib = 1;
-            for (int i = 0; i < d; ++i) {
-                for (int c = 0; c < v[i]; ++c, ++ia) ra += binom(a.bin, dm[i] + ia - 1, ia);
-                for (int c = v[i]; c < s[i]; ++c, ++ib) rb += binom(a.bin, dm[i] + ib - 1, ib);
+        const bool pick_a = ka <= kb;
+        const int q = pick_a ? ka : kb;
+        for (int j = 0; j < q; ++j) c[j] = j;
+        for (;;) {
+            bool canonical = true;
+            for (int j = 0; j < q; ++j)
+                if (c[j] > 0 && x[c[j]] == x[c[j] - 1] && (j == 0 || c[j - 1] != c[j] - 1)) { canonical = false; break; }
+            if (canonical) {
+                // colex ranks of the picked photons and of the rest: sum over photons, ascending, of C(mode + i - 1, i)
+                uint64_t r_sel = 0, r_rest = 0;
+                int is = 0, ir = 1;
+                for (int p = 0; p < kt; ++p) {
+                    if (is < q && c[is] == p) { ++is; r_sel += binom(a.bin, x[p] + is - 1, is); }
+                    else { r_rest += binom(a.bin, x[p] + ir - 1, ir); ++ir; }
+                }
+                const uint64_t ra = pick_a ? r_sel : r_rest, rb = pick_a ? r_rest : r_sel;
+                acc += a.A[a.off[ka] + ra] * a.B[a.off[kb] + rb];
             }
-            acc += a.A[a.off[ka] + ra] * a.B[a.off[kb] + rb];
+            int j = q - 1;  // next combination in lexicographic order
+            while (j >= 0 && c[j] == kt - q + j) --j;
+            if (j < 0) break;
+            ++c[j];
+            for (int l = j + 1; l < q; ++l) c[l] = c[l - 1] + 1;
         }
-        int i = 0;  // odometer
-        while (i < d && v[i] == s[i]) { ka -= v[i]; v[i] = 0; ++i; }
-        if (i == d) break;
-        v[i] += 1;
-        ka += 1;
     }
     a.out[o] = acc;
 }

@@ -50,9 +50,11 @@ for (m, n, seed, run_oracle) in [(8, 4, 1, True), (12, 6, 2, False), (16, 8, 4, 
     circ = Circ(U, m)
     inputs = inputs_for(m, n)
     pdist_calc(circ, dict(list(inputs.items())[:3]), b)  # warm-up (context, kernels)
-    t0 = time.perf_counter()
-    res = pdist_calc(circ, inputs, b)
-    dt = time.perf_counter() - t0
+    dt = 1e30
+    for _ in range(2):  # best of two: the first pass also pays CUDA's lazy kernel loading
+        t0 = time.perf_counter()
+        res = pdist_calc(circ, inputs, b)
+        dt = min(dt, time.perf_counter() - t0)
     print(f"m={m} n={n}: {len(inputs)} annotated inputs -> {len(res)} outputs, sum={res.vals_array.sum():.12f}, "
           f"{res.n_convolutions} convolutions, {dt * 1e3:.1f} ms on the device path")
     if run_oracle:
