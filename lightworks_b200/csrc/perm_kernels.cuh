@@ -25,6 +25,9 @@ constexpr int K1_THREADS = 256;
 #ifndef LWB_MINB
 #define LWB_MINB 1
 #endif
+#ifndef LWB_K2_COFF
+#define LWB_K2_COFF 19  /* K2 chunk bits C = clamp(N - LWB_K2_COFF, 3, 7); 19 vs 21: n = 24 runs 13 % faster, others equal (profiles/r01_k2_chunk_sweep.log) */
+#endif
 
 // Work split shared by all kernels: LOG_L lanes-per-permanent exponent and chunk bits.
 template <int N, int LOG_L>
@@ -237,7 +240,7 @@ template <int N>
 struct K2Shape {
     // chunk bits: every lane gets a contiguous range of ~28+ chunks (glynn_range), so C only has to keep the
     // lane-specific boundary flips rare; small n cannot fill the GPU anyway (use the batched kernel there)
-    static constexpr int C0 = N - 21;
+    static constexpr int C0 = N - LWB_K2_COFF;
     static constexpr int CC = C0 < 3 ? 3 : (C0 > 7 ? 7 : C0);
     static constexpr int C = CC > N - 1 ? (N - 1 < 1 ? 1 : N - 1) : CC;
     static constexpr int U = C < LWB_U2(N) ? C : LWB_U2(N);
