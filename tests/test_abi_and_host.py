@@ -43,6 +43,26 @@ def test_compute_calls_fail_loudly_without_gpu():
         _lib.Context(0)
     with pytest.raises(lb.BackendError):  # no silent CPU fallback in the product path
         lb.PermanentBackend().probability_amplitude(np.eye(2), [1, 0], [1, 0])
+    circ = lb.CompiledCircuitView(np.eye(2))
+    with pytest.raises(lb.BackendError):  # nor in the widened rows: sampling and source-statistics combination
+        lb.PermanentBackend().sample_outputs(circ, [1, 0], 10, seed=1)
+    with pytest.raises(lb.BackendError):
+        lb.pdist_calc(circ, {(1, 0): 1.0}, lb.SLOSBackend())
+
+
+def test_keyspace_layout_host():
+    """Dense-distribution key space (include/lwb200.h): photon-number blocks side by side, fock_basis order inside."""
+    m, kmax = 4, 3
+    size = _lib.keyspace_size(m, kmax)
+    assert size == sum(lb.fock_count(m, k) for k in range(kmax + 1))
+    states = _lib.keyspace_states(m, kmax, np.arange(size))
+    expect = [s for k in range(kmax + 1) for s in O.py_fock_basis(m, k)]
+    assert states.tolist() == expect
+    for i, s in enumerate(expect):
+        assert _lib.keyspace_index(s) == i
+        assert _lib.keyspace_state(m, kmax, i).tolist() == s
+    with pytest.raises(ValueError):
+        _lib.keyspace_state(m, kmax, size)
 
 
 @pytest.mark.parametrize("rec", golden().of_kind("fock"), ids=lambda r: f"m{r['m']}n{r['n']}")
