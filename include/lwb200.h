@@ -176,6 +176,17 @@ int lwb_dist_download(lwb_handle h, int slot, double* dense);
 int lwb_dist_sample(lwb_handle h, int slot, const double* uniform, uint64_t n_samples, uint64_t* index, double* total);
 int lwb_dist_free(lwb_handle h, int slot);
 
+/* ---- imperfect-source input statistics (host only) ------------------------------------------------
+ * Source._build_statistics (emulator/components/source.py:134-161 with :163-406): every input the source can emit
+ * for the target `state` and its probability, thresholded (p >= threshold) and renormalised, in the reference's
+ * dict order.  Entry k is two occupation vectors: group_occ[k] = photons per mode that share label 0 (mutually
+ * indistinguishable), single_occ[k] = photons per mode that carry a label of their own; *annotated = 0 when the
+ * reference would return plain States (purity = indistinguishability = 1: group_occ is the state).  Returns
+ * LWB_E_LIMIT with *count set when cap is too small. */
+int lwb_source_statistics(int n_modes, const uint8_t* state, double purity, double brightness,
+                          double indistinguishability, double threshold, uint64_t cap, uint8_t* group_occ,
+                          uint8_t* single_occ, double* probs, uint64_t* count, int* annotated);
+
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */
 int lwb_fp64_peak(lwb_handle h, double* flops_per_s);

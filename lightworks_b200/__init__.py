@@ -21,6 +21,7 @@ from ._lib import (  # noqa: F401
     set_tuning,
     slos_rank,
     slos_unrank,
+    source_statistics,
 )
 
 from .backends import (  # noqa: E402, F401
@@ -30,6 +31,7 @@ from .backends import (  # noqa: E402, F401
     SLOSBackend,
     install,
     set_convolve_on_gpu,
+    set_native_source_statistics,
     uninstall,
 )
 from .convolution import DistributionAlgebra, pdist_calc  # noqa: E402, F401

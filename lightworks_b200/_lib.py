@@ -81,6 +81,7 @@ SIGNATURES = {
     "lwb_dist_download": (_i, [_vp, _i, _vp]),
     "lwb_dist_sample": (_i, [_vp, _i, _vp, _u64, _vp, _pdbl]),
     "lwb_dist_free": (_i, [_vp, _i]),
+    "lwb_source_statistics": (_i, [_i, _vp, _dbl, _dbl, _dbl, _dbl, _u64, _vp, _vp, _vp, _pu64, _pi]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
     "lwb_fp64_probe": (_i, [_vp, _i, _pdbl]),
 }
@@ -195,6 +196,48 @@ def keyspace_states(n_modes: int, kmax: int, indices) -> np.ndarray:
     out = np.zeros((len(idx), n_modes), dtype=np.uint8)
     check(cdll().lwb_keyspace_states(n_modes, kmax, ptr(idx), len(idx), ptr(out)))
     return out
+
+
+def source_statistics(state, purity=1.0, brightness=1.0, indistinguishability=1.0, probability_threshold=1e-9):
+    """Source(purity, brightness, indistinguishability, probability_threshold)._build_statistics(state)
+    (emulator/components/source.py:134-161) enumerated natively on the host.  Returns (annotated, entries) with
+    entries = [(state, p), ...] in the reference's dict order; a state is a tuple of per-mode label tuples
+    (AnnotatedState.s, labels renumbered by first appearance as _remap_distribution does) when `annotated`,
+    else a plain occupation tuple (State.s)."""
+    s = _u8(state)
+    m = len(s)
+    cap = 1 << 12
+    while True:
+        g = np.zeros((cap, m), dtype=np.uint8)
+        b = np.zeros((cap, m), dtype=np.uint8)
+        p = np.zeros(cap, dtype=np.float64)
+        cnt, ann = C.c_uint64(0), C.c_int(0)
+        rc = cdll().lwb_source_statistics(m, ptr(s), float(purity), float(brightness), float(indistinguishability),
+                                          float(probability_threshold), cap, ptr(g), ptr(b), ptr(p), C.byref(cnt),
+                                          C.byref(ann))
+        if rc == LWB_E_LIMIT and cnt.value > cap:
+            cap = int(cnt.value)
+            continue
+        check(rc)
+        break
+    k = int(cnt.value)
+    if not ann.value:
+        return False, [(tuple(int(v) for v in g[i]), float(p[i])) for i in range(k)]
+    out = []
+    for i in range(k):
+        nxt, zero, modes = 0, None, []
+        for j in range(m):
+            labels = []
+            for _ in range(int(g[i, j])):  # the shared label gets its number at its first appearance
+                if zero is None:
+                    zero, nxt = nxt, nxt + 1
+                labels.append(zero)
+            for _ in range(int(b[i, j])):
+                labels.append(nxt)
+                nxt += 1
+            modes.append(tuple(sorted(labels)))
+        out.append((tuple(modes), float(p[i])))
+    return True, out
 
 
 class DeviceDistribution:

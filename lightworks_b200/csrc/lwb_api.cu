@@ -33,6 +33,9 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
+namespace lwb {
+int set_error(int code, const char* msg) { return fail(code, "%s", msg); }  // for the host-only units (source_stats.cpp)
+}  // namespace lwb
 #define CU(call)                                                                                 \
     do {                                                                                         \
         cudaError_t e_ = (call);                                                                 \

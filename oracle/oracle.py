@@ -443,3 +443,81 @@ def pdist_func(backend: str = "permanent", threshold: float = 1e-9):
         return {tuple(int(v) for v in k): float(p) for k, p in zip(keys, vals)}
 
     return f
+
+
+# ---- imperfect-source input statistics (second half) ---------------------
+def py_build_statistics(state, purity=1.0, brightness=1.0, indistinguishability=1.0, probability_threshold=1e-9):
+    """Source._build_statistics (emulator/components/source.py:134-161) restated with tuples: returns
+    (annotated, dict) in the reference's dict order.  States are occupation tuples (basic method, :163-224) or
+    tuples of per-mode label tuples (full method, :226-391); thresholding and renormalisation as :394-406."""
+    state = tuple(int(v) for v in state)
+    n_modes = len(state)
+    if purity == 1 and indistinguishability == 1:                         # :155-157
+        stats: list = []
+        for mode, count in enumerate(state):                              # :177-209
+            for _ in range(count):
+                sub_s = [(brightness, tuple(1 if mode == j else 0 for j in range(n_modes)))]
+                if brightness < 1:
+                    sub_s.append((1 - brightness, tuple([0] * n_modes)))
+                if not stats:
+                    stats = sub_s
+                else:
+                    stats = [(p1 * p2, tuple(x + y for x, y in zip(s1, s2))) for p1, s1 in stats for p2, s2 in sub_s]
+        dist: dict = {}
+        for p, s in stats:                                                # :211-218
+            dist[s] = dist.get(s, 0) + p if s in dist else p
+        if not dist:                                                      # :221-223
+            dist[state] = 1.0
+        annotated = False
+    else:
+        if purity <= 0.5:                                                 # :442-443
+            raise ValueError("Purity values below 0.5 not supported.")
+        if purity < 1:                                                    # :444-447
+            g2 = 1 - purity
+            b = 2 * (1 - (1 / g2))
+            p1 = 1 - (-b - (b**2 - 4) ** 0.5) / 2
+        else:
+            p1 = 1
+        counter = [1]
+
+        def single_photon():                                              # :353-391
+            nu, p_i = brightness, indistinguishability**0.5
+            p_d, p2 = 1 - p_i, 1 - p1
+            c0 = 1 - nu * (p1 + p2 * nu + 2 * (1 - nu) * p2)
+            c1 = p_i * nu * (p1 + (1 - nu) * p2)
+            c1d = p_d * nu * (p1 + (1 - nu) * p2)
+            c1dp = nu * (1 - nu) * p2
+            c12d = nu**2 * p_i * p2
+            c1d2d = nu**2 * p_d * p2
+            dpc, mpc = counter[0], counter[0] + 1
+            counter[0] += 2
+            to_add = [([], c0), ([0], c1), ([dpc], c1d), ([mpc], c1dp), ([0, mpc], c12d), ([dpc, mpc], c1d2d)]
+            return [(s, p) for s, p in to_add if p > 0]
+
+        def single_mode(n):                                               # :318-351
+            if n == 0:
+                return {((),): 1.0}
+            mode_dist: list = []
+            for _ in range(n):
+                calc = single_photon()
+                mode_dist = calc if not mode_dist else [(d1[0] + d2[0], d1[1] * d2[1]) for d1 in mode_dist for d2 in calc]
+            out: dict = {}
+            for s, p in mode_dist:
+                key = (tuple(sorted(s)),)
+                out[key] = out[key] + p if key in out else p
+            return out
+
+        full: dict = {}
+        for n in state:                                                   # :292-316 (empty-mode grouping is an optimisation)
+            calc = single_mode(n)
+            full = calc if not full else {s1 + s2: p1_ * p2_ for s1, p1_ in full.items() for s2, p2_ in calc.items()}
+        dist = {}
+        for s, p in full.items():                                         # :252-283
+            labels = list(dict.fromkeys(lab for mode in s for lab in mode))
+            mapping = {lab: i for i, lab in enumerate(labels)}
+            key = tuple(tuple(sorted(mapping[lab] for lab in mode)) for mode in s)
+            dist[key] = dist[key] + p if key in dist else p
+        annotated = True
+    kept = {s: p for s, p in dist.items() if p >= probability_threshold}   # :401-406
+    total = sum(kept.values())
+    return annotated, {s: p / total for s, p in kept.items()}

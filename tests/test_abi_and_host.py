@@ -179,3 +179,18 @@ def test_cumulative_work_is_exact_and_cuts_balance():
         c0 = sharding.STATE_OVERHEAD_TERMS
         w = [sharding.cumulative_work(m, n, b, c0) - sharding.cumulative_work(m, n, a, c0) for a, b in ranges]
         assert max(w) / (sum(w) / world) < 1.0001
+
+
+@pytest.mark.reference
+def test_reference_source_suite_with_native_statistics():
+    """The reference's own tests/emulator/source_test.py with Source._build_statistics answered by
+    lwb_source_statistics (lightworks_b200.install(); host only, no GPU involved)."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "oracle.run_reference_tests", "--b200", "emulator/source_test.py"], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
+    assert " passed" in r.stdout
