@@ -44,12 +44,13 @@ def _is_annotated(state) -> bool:
 class DistributionAlgebra:
     """Device-resident per-input distributions of one circuit and cached partial products."""
 
-    def __init__(self, ctx, circuit, backend_id, threshold: float, dtype=_lib.LWB_C128, max_cached: int = 4096):
+    def __init__(self, ctx, circuit, backend_id, threshold: float, dtype=_lib.LWB_C128, max_cached: int = 4096,
+                 max_cached_bytes: int = 8 << 30):
         self.ctx, self.circuit = ctx, circuit
         self.backend_id, self.threshold, self.dtype = backend_id, threshold, dtype
         self._unique: dict[tuple, _lib.DeviceDistribution] = {}
         self._products: dict[tuple, _lib.DeviceDistribution] = {}
-        self._max_cached = max_cached
+        self._max_cached, self._max_bytes, self._bytes = max_cached, max_cached_bytes, 0
         self.n_convolutions = 0
 
     def unique(self, state: tuple) -> _lib.DeviceDistribution:
@@ -74,8 +75,10 @@ class DistributionAlgebra:
             return self.unique(chain[0])
         d = self.product(list(chain[:-1])) @ self.unique(chain[-1])
         self.n_convolutions += 1
-        if len(self._products) >= self._max_cached:
-            self._products.pop(next(iter(self._products)))
+        self._bytes += 8 * d.size
+        while self._products and (len(self._products) >= self._max_cached or self._bytes > self._max_bytes):
+            old = self._products.pop(next(iter(self._products)))  # oldest first; recomputed if needed again
+            self._bytes -= 8 * old.size
         self._products[chain] = d
         return d
 
