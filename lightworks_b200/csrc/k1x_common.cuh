@@ -1,5 +1,6 @@
-// k1x_common.cuh -- data structures and the statically unrolled kernel of the multiplicity-aware permanent
-// walk (see k1x.h), shared by k1x.cu (host pipeline, generic kernel) and the k1xs_g*.cu instantiation units.
+// k1x_common.cuh -- data structures, the two walks (generic table-driven, static Gray chunk) and the fused kernel of
+// the multiplicity-aware permanent (see k1x.h); shared by k1x.cu (host pipeline, bucketing kernels, n <= 6) and the
+// k1xs_g*.cu instantiation units (n = 7..16).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,7 +33,7 @@ struct TypeMeta {
     int prog_off;  // first Step of this type in the program array
     int factor;    // 2 when the v -> s-v symmetry halves the sum, else 1
     int ns;        // singly occupied rows (the last ns slots)
-    int klass;     // -1: generic table-driven kernel; C >= 2: k1x_static_kernel<N, C>, C = ns - 1
+    int klass;     // -1: generic table-driven walk; C >= 2: k1x_static_walk<N, C>, C = ns - 1
     int s[K1X_MAX_N];  // multiplicities, descending
 };
 struct Step {
