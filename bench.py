@@ -449,7 +449,12 @@ def main() -> int:  # noqa: PLR0915
                 "achieved": alg / (k_ms * 1e-3) / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
                 "frac": alg / (k_ms * 1e-3) / peak, "executed_frac": executed / (k_ms * 1e-3) / peak,
                 "average_terms_per_permanent": avg_terms, "terms_expanded": 2 ** (N_PH - 1),
-                "traffic": traffic, "kernel_ms": k_ms, "flops_per_unit": flops_per_perm(N_PH), "units_per_launch": cnt,
+                "traffic": traffic,
+                "traffic_note": "DRAM bytes of one fused-kernel launch (ncu): 4x the 740 MB of algorithmic output because the "
+                                "probabilities leave in bucket (multiplicity-pattern) order as scattered 8-byte stores "
+                                "(partial-sector fills) and the 370 MB bucket index is read; 3.1 GB per 98 ms = 31 GB/s, "
+                                "0.5 % of the HBM peak - the kernel is FP64-bound",
+                "kernel_ms": k_ms, "flops_per_unit": flops_per_perm(N_PH), "units_per_launch": cnt,
                 "peak_source": peak_src,
                 "note": "frac uses the reference algorithm's flop count per permanent, so a walk that skips the repeated-row "
                         "terms of bunched outputs can exceed the 0.57 register-file ceiling of the expanded-row kernel; "
