@@ -34,7 +34,7 @@ from .backends import (  # noqa: E402, F401
     set_native_source_statistics,
     uninstall,
 )
-from .convolution import DistributionAlgebra, pdist_calc  # noqa: E402, F401
+from .convolution import DistributionAlgebra, pdist_calc, sample_source_outputs  # noqa: E402, F401
 from .state import CompiledCircuitView, State  # noqa: E402, F401
 
 __version__ = "0.1.0"

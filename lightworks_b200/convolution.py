@@ -90,8 +90,11 @@ class DistributionAlgebra:
         return d
 
 
-def pdist_calc(circuit, inputs, backend):
-    """probability_distribution.py:25-73 (State inputs) and :78-164 (AnnotatedState inputs) on the device."""
+def pdist_calc(circuit, inputs, backend, keep_on_device: bool = False):
+    """probability_distribution.py:25-73 (State inputs) and :78-164 (AnnotatedState inputs) on the device.
+    keep_on_device: return the accumulated DeviceDistribution (dense over K(n_modes, max photons)) instead of
+    downloading it; not available where the reference patches the vacuum entry afterwards (State inputs on a
+    lossy circuit, :70-73)."""
     from .backends import LazyDistribution, _threshold
 
     ctx = backend.ctx
@@ -130,6 +133,11 @@ def pdist_calc(circuit, inputs, backend):
             others.add_scaled(prob, alg.product(rest) if rest else alg.vacuum())
         acc.add_scaled(1.0, alg.unique(big) @ others)
         alg.n_convolutions += 1
+    if keep_on_device:
+        if not annotated and getattr(circuit, "loss_modes", 0) > 0:
+            raise ValueError("keep_on_device: the vacuum rule of probability_distribution.py:70-73 needs the host copy")
+        acc.n_convolutions = alg.n_convolutions
+        return acc
     dense = acc.to_numpy()
     if not annotated and getattr(circuit, "loss_modes", 0) > 0:
         # :70-73: `if total_prob < 1: pdist[vacuum] = 1 - total_prob` OVERWRITES an existing vacuum entry.  When the
@@ -144,3 +152,42 @@ def pdist_calc(circuit, inputs, backend):
     out = LazyDistribution(keys, dense[idx])
     out.n_convolutions = alg.n_convolutions
     return out
+
+
+def sample_source_outputs(circuit, input_state, n_samples: int, backend, purity: float = 1.0, brightness: float = 1.0,
+                          indistinguishability: float = 1.0, probability_threshold: float = 1e-9,
+                          detector_efficiency: float = 1.0, p_dark: float = 0.0, photon_counting: bool = True, seed=None):
+    """`Sampler(circuit, input_state, n_samples, source=Source(...), detector=Detector(...), sampling_mode="input")`
+    (simulation/sampler.py:144-237) for circuits without heralds or post-selection, with the output distribution of the
+    imperfect source built, kept and sampled on the device:
+
+      Source._build_statistics            -> lwb_source_statistics (host, components/source.py:134-406)
+      pdist_calc                          -> dense distributions + merge-convolution (probability_distribution.py:25-164)
+      _gen_samples_from_dist              -> lwb_dist_sample (sampler.py:329-349; uniforms from numpy's default_rng(seed))
+      Detector._get_output per sample     -> vectorised: binomial thinning with `efficiency`, one dark count per mode
+                                             with probability p_dark, threshold detection (components/detector.py:101-135)
+
+    Returns {State: count} like SamplingResult.  The drawn output states follow the reference's distribution; the
+    detector draws use numpy's generator instead of Python's `random`, so counts are statistically, not bitwise, equal to
+    the reference's for a seed."""
+    from collections import Counter
+
+    from .backends import _as_list, _state_cls
+
+    ins = _as_list(input_state)
+    n_modes = circuit.n_modes
+    if len(ins) != n_modes:
+        raise ValueError("input state length does not match the circuit")
+    _annotated, entries = _lib.source_statistics(ins, purity, brightness, indistinguishability, probability_threshold)
+    acc = pdist_calc(circuit, dict(entries), backend, keep_on_device=True)
+    rng = np.random.default_rng(seed)
+    idx, _total = acc.sample(rng.random(int(n_samples)))
+    uniq, inverse = np.unique(idx, return_inverse=True)
+    out = _lib.keyspace_states(n_modes, acc.kmax, uniq)[inverse].astype(np.int64)  # one row per sample
+    if detector_efficiency < 1:
+        out = rng.binomial(out, detector_efficiency)
+    if p_dark > 0:
+        out = out + (rng.random(out.shape) < p_dark)
+    if not photon_counting:
+        out = np.minimum(out, 1)
+    return {_state_cls(list(k)): c for k, c in Counter(map(tuple, out.tolist())).items()}

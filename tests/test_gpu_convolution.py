@@ -171,3 +171,28 @@ def test_device_distribution_sampling(lb, ctx):
     assert total == pytest.approx(dense.sum(), rel=1e-12)
     ref = O.sample_indices(dense, u)
     assert np.count_nonzero(ref != idx) <= 1
+
+
+def test_sample_source_outputs_statistics(lb):
+    """Whole noisy Sampler chain on the device (source statistics -> convolution -> sampling -> detector model): the
+    empirical mean photon number per mode against the exact expectation from the oracle's distribution of the same
+    imperfect source (efficiency-thinned), within 5 standard errors; and reproducibility for a seed."""
+    m, ins = 6, [1, 0, 1, 1, 0, 0]
+    U = O.random_unitary(m, 17)  # noqa: N806
+    circ = _Circ(U, m)
+    kw = dict(purity=0.95, brightness=0.85, indistinguishability=0.9)
+    _, inputs = O.py_build_statistics(ins, **kw)
+    ref = O.py_annotated_pdist_calc(circ, inputs, O.pdist_func("permanent"))
+    eff, n = 0.8, 40000
+    expect = eff * sum(p * np.array(k, dtype=float) for k, p in ref.items())
+    second = sum(p * (eff * (1 - eff) * np.array(k, dtype=float) + (eff * np.array(k, dtype=float)) ** 2) for k, p in ref.items())
+    sigma = np.sqrt(np.maximum(second - expect**2, 1e-12) / n)
+    b = lb.PermanentBackend()
+    got = lb.sample_source_outputs(circ, ins, n, b, detector_efficiency=eff, seed=5, **kw)
+    assert sum(got.values()) == n
+    mean = sum(c * np.array(k.s, dtype=float) for k, c in got.items()) / n
+    assert np.all(np.abs(mean - expect) < 5 * sigma + 1e-9), (mean, expect, sigma)
+    again = lb.sample_source_outputs(circ, ins, n, b, detector_efficiency=eff, seed=5, **kw)
+    assert {tuple(k.s): c for k, c in got.items()} == {tuple(k.s): c for k, c in again.items()}
+    clicks = lb.sample_source_outputs(circ, ins, 2000, b, photon_counting=False, p_dark=0.01, seed=6, **kw)
+    assert all(max(k.s) <= 1 for k in clicks)

@@ -31,3 +31,11 @@ vals = res.vals_array
 print(f"pdist_calc on the device: {t3 - t2:.2f} s, {res.n_convolutions} convolutions, {len(vals)} output states, "
       f"sum = {vals.sum():.12f}, by photon number: "
       f"{ {int(k): float(vals[res.keys_array.sum(axis=1) == k].sum()) for k in range(0, 12)} }", flush=True)
+t4 = time.perf_counter()
+counts = lb.sample_source_outputs(circ, [1] * n + [0] * (m - n), 1_000_000, b, purity=0.99, brightness=0.9,
+                                  indistinguishability=0.95, detector_efficiency=0.9, seed=1)
+t5 = time.perf_counter()
+tot = sum(counts.values())
+mean_detected = sum(c * sum(k.s) for k, c in counts.items()) / tot
+print(f"noisy Sampler on the device (source + convolution + 10^6 samples + detector efficiency 0.9): {t5 - t4:.2f} s, "
+      f"{len(counts)} distinct outcomes, mean detected photons {mean_detected:.4f}", flush=True)
