@@ -198,15 +198,13 @@ def keyspace_states(n_modes: int, kmax: int, indices) -> np.ndarray:
     return out
 
 
-def source_statistics(state, purity=1.0, brightness=1.0, indistinguishability=1.0, probability_threshold=1e-9):
-    """Source(purity, brightness, indistinguishability, probability_threshold)._build_statistics(state)
-    (emulator/components/source.py:134-161) enumerated natively on the host.  Returns (annotated, entries) with
-    entries = [(state, p), ...] in the reference's dict order; a state is a tuple of per-mode label tuples
-    (AnnotatedState.s, labels renumbered by first appearance as _remap_distribution does) when `annotated`,
-    else a plain occupation tuple (State.s)."""
+def source_classes(state, purity=1.0, brightness=1.0, indistinguishability=1.0, probability_threshold=1e-9):
+    """lwb_source_statistics as arrays: (annotated, group_occ uint8[K, m], single_occ uint8[K, m], probs float64[K]) in
+    the reference's dict order (include/lwb200.h): group_occ = photons per mode sharing label 0, single_occ = photons
+    per mode carrying a label of their own."""
     s = _u8(state)
     m = len(s)
-    cap = 1 << 12
+    cap = 1 << 16  # a too small capacity costs a second enumeration
     while True:
         g = np.zeros((cap, m), dtype=np.uint8)
         b = np.zeros((cap, m), dtype=np.uint8)
@@ -221,22 +219,33 @@ def source_statistics(state, purity=1.0, brightness=1.0, indistinguishability=1.
         check(rc)
         break
     k = int(cnt.value)
-    if not ann.value:
-        return False, [(tuple(int(v) for v in g[i]), float(p[i])) for i in range(k)]
+    return bool(ann.value), g[:k], b[:k], p[:k]
+
+
+def source_statistics(state, purity=1.0, brightness=1.0, indistinguishability=1.0, probability_threshold=1e-9):
+    """Source(purity, brightness, indistinguishability, probability_threshold)._build_statistics(state)
+    (emulator/components/source.py:134-161) enumerated natively on the host.  Returns (annotated, entries) with
+    entries = [(state, p), ...] in the reference's dict order; a state is a tuple of per-mode label tuples
+    (AnnotatedState.s, labels renumbered by first appearance as _remap_distribution does) when `annotated`,
+    else a plain occupation tuple (State.s)."""
+    ann, g, b, p = source_classes(state, purity, brightness, indistinguishability, probability_threshold)
+    m = g.shape[1]
+    if not ann:
+        return False, [(tuple(int(v) for v in row), float(q)) for row, q in zip(g, p)]
     out = []
-    for i in range(k):
+    for gi, bi, q in zip(g.tolist(), b.tolist(), p.tolist()):
         nxt, zero, modes = 0, None, []
         for j in range(m):
             labels = []
-            for _ in range(int(g[i, j])):  # the shared label gets its number at its first appearance
+            if gi[j]:  # the shared label gets its number at its first appearance
                 if zero is None:
                     zero, nxt = nxt, nxt + 1
-                labels.append(zero)
-            for _ in range(int(b[i, j])):
-                labels.append(nxt)
-                nxt += 1
-            modes.append(tuple(sorted(labels)))
-        out.append((tuple(modes), float(p[i])))
+                labels += [zero] * gi[j]
+            if bi[j]:
+                labels += range(nxt, nxt + bi[j])
+                nxt += bi[j]
+            modes.append(tuple(labels))
+        out.append((tuple(modes), q))
     return True, out
 
 

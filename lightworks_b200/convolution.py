@@ -41,6 +41,35 @@ def _is_annotated(state) -> bool:
     return len(s) > 0 and isinstance(s[0], (list, tuple))
 
 
+class SourceClasses:
+    """The inputs of an imperfect source in array form (lwb_source_statistics): per input the occupation vector of the
+    mutually indistinguishable photons and of the photons that carry a label of their own.  Accepted by pdist_calc in
+    place of the reference's dict[AnnotatedState, p]; skips building and re-parsing label lists."""
+
+    def __init__(self, annotated: bool, group_occ: np.ndarray, single_occ: np.ndarray, probs: np.ndarray):
+        self.annotated, self.group_occ, self.single_occ, self.probs = annotated, group_occ, single_occ, probs
+
+    @classmethod
+    def from_source(cls, state, purity=1.0, brightness=1.0, indistinguishability=1.0, probability_threshold=1e-9):
+        return cls(*_lib.source_classes(state, purity, brightness, indistinguishability, probability_threshold))
+
+    def __len__(self):
+        return len(self.probs)
+
+    def combos(self, n_modes: int) -> list:
+        """[(list of per-label occupation tuples, p)]: the group (if any photons) and one unit vector per single."""
+        if self.group_occ.shape[1] != n_modes:
+            raise ValueError("source statistics and circuit have different mode counts")
+        eye = [tuple(1 if i == j else 0 for i in range(n_modes)) for j in range(n_modes)]
+        out = []
+        for g, b, p in zip(self.group_occ.tolist(), self.single_occ.tolist(), self.probs.tolist()):
+            states = [tuple(g)] if any(g) or not any(b) else []
+            for j, c in enumerate(b):
+                states += [eye[j]] * c
+            out.append((states, p))
+        return out
+
+
 class DistributionAlgebra:
     """Device-resident per-input distributions of one circuit and cached partial products."""
 
@@ -100,17 +129,21 @@ def pdist_calc(circuit, inputs, backend, keep_on_device: bool = False):
     ctx = backend.ctx
     n_modes = circuit.n_modes
     alg = DistributionAlgebra(ctx, circuit, backend._backend_id, _threshold(), backend._dtype)
-    inputs = dict(inputs)
-    if not inputs:
+    if not isinstance(inputs, SourceClasses):
+        inputs = dict(inputs)
+    if not len(inputs):
         return LazyDistribution(np.zeros((0, n_modes), dtype=np.uint8), np.zeros(0))
-    annotated = _is_annotated(next(iter(inputs)))
-    combos = []
-    for istate, prob in inputs.items():
-        if annotated:
-            combos.append((_labels_to_states(istate, n_modes), float(prob)))
-        else:
-            s = tuple(istate.s if hasattr(istate, "s") else istate)
-            combos.append(([s[:n_modes] if len(s) > n_modes else s], float(prob)))
+    if isinstance(inputs, SourceClasses):
+        annotated, combos = inputs.annotated, inputs.combos(n_modes)
+    else:
+        annotated = _is_annotated(next(iter(inputs)))
+        combos = []
+        for istate, prob in inputs.items():
+            if annotated:
+                combos.append((_labels_to_states(istate, n_modes), float(prob)))
+            else:
+                s = tuple(istate.s if hasattr(istate, "s") else istate)
+                combos.append(([s[:n_modes] if len(s) > n_modes else s], float(prob)))
     kmax = max(sum(sum(s) for s in states) for states, _ in combos)
     acc = ctx.dist_zeros(n_modes, kmax)
     # sum_inputs p * D_G (*) prod(rest) = sum_G D_G (*) ( sum_rest p * prod(rest) ) by linearity: the inputs are grouped
@@ -178,8 +211,8 @@ def sample_source_outputs(circuit, input_state, n_samples: int, backend, purity:
     n_modes = circuit.n_modes
     if len(ins) != n_modes:
         raise ValueError("input state length does not match the circuit")
-    _annotated, entries = _lib.source_statistics(ins, purity, brightness, indistinguishability, probability_threshold)
-    acc = pdist_calc(circuit, dict(entries), backend, keep_on_device=True)
+    classes = SourceClasses.from_source(ins, purity, brightness, indistinguishability, probability_threshold)
+    acc = pdist_calc(circuit, classes, backend, keep_on_device=True)
     rng = np.random.default_rng(seed)
     idx, _total = acc.sample(rng.random(int(n_samples)))
     uniq, inverse = np.unique(idx, return_inverse=True)

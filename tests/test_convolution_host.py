@@ -121,3 +121,28 @@ def test_work_balanced_pieces_partition():
     for x in w:
         assert x[0] / sum(x) == pytest.approx(0.6, abs=1e-4) and x[2] / sum(x) == pytest.approx(0.1, abs=1e-4)
     assert sharding.work_balanced_ranges(6, 3, 2, [0.5, 0.5]) == [[(0, 14), (14, 28)], [(28, 42), (42, 56)]]  # uniform below n = 7
+
+
+def test_source_classes_path_equals_label_path():
+    """pdist_calc fed with SourceClasses (arrays from lwb_source_statistics) against the same statistics as a dict of
+    annotated label tuples: identical distributions (host orchestration on the numpy stand-in)."""
+    m, ins = 5, [1, 1, 0, 2, 0]
+    circ = lb.CompiledCircuitView(O.random_unitary(m, 23))
+    kw = dict(purity=0.9, brightness=0.8, indistinguishability=0.85, probability_threshold=1e-5)
+    for backend in ("permanent", "slos"):
+        ann, entries = _lib.source_statistics(ins, **kw)
+        assert ann
+        a = conv.pdist_calc(circ, dict(entries), _FakeBackend(backend))
+        b = conv.pdist_calc(circ, conv.SourceClasses.from_source(ins, **kw), _FakeBackend(backend))
+        assert np.array_equal(a.keys_array, b.keys_array)
+        assert np.allclose(a.vals_array, b.vals_array, rtol=1e-12, atol=0)
+        # and against the oracle's restatement of the whole reference chain
+        _, inputs = O.py_build_statistics(ins, **kw)
+        ref = O.py_annotated_pdist_calc(circ, inputs, O.pdist_func(backend))
+        got = {tuple(int(v) for v in k): float(p) for k, p in zip(b.keys_array, b.vals_array)}
+        assert set(got) == set(ref) and all(got[k] == pytest.approx(v, rel=1e-10) for k, v in ref.items())
+    # brightness-only source: plain State inputs through the same class
+    basic = conv.SourceClasses.from_source([1, 0, 1, 0, 0], brightness=0.7)
+    assert not basic.annotated and len(basic) == 4
+    d = conv.pdist_calc(lb.CompiledCircuitView(O.random_unitary(5, 3)), basic, _FakeBackend("permanent"))
+    assert d.vals_array.sum() == pytest.approx(1.0, abs=1e-8)
