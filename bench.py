@@ -171,7 +171,6 @@ def run_reference_arm(args) -> int:
         # PermanentBackend.probability per output state, exactly the loop body of permanent.py:145-150
         refshim.install()
         from lightworks.emulator.backends.permanent import PermanentBackend as RefPermanent  # noqa: PLC0415
-        from lightworks.emulator.utils.state import fock_basis  # noqa: F401, PLC0415
 
         sample = args.ref_sample or 20000
         outs = O.fock_basis(M, N_PH, limit=sample).tolist()  # same order as fock_basis(24,10)[:sample]

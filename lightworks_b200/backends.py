@@ -18,7 +18,7 @@ from collections.abc import Mapping
 import numpy as np
 
 from . import _lib
-from .state import CompiledCircuitView, State
+from .state import State
 
 _DTYPES = {"complex128": _lib.LWB_C128, "complex64": _lib.LWB_C64, _lib.LWB_C128: _lib.LWB_C128, _lib.LWB_C64: _lib.LWB_C64}
 
@@ -266,7 +266,7 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
     from lightworks.emulator.backends.fock_backend import FockBackend
     from lightworks.emulator.backends.permanent import PermanentBackend as RefPermanent
     from lightworks.emulator.backends.slos import SLOSBackend as RefSLOS
-    from lightworks.emulator.simulation import AnalyzerRunner, SamplerRunner, SimulatorRunner  # noqa: F401
+    from lightworks.emulator.simulation import AnalyzerRunner
     from lightworks.emulator.utils.exceptions import BackendError as LwBackendError
     from lightworks.emulator.utils.sim import check_photon_numbers
     from lightworks.sdk.results import SimulationResult

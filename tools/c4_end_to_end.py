@@ -7,8 +7,6 @@ The reference needs 131 s for the first phase alone and hours for the second (SU
 import sys
 import time
 
-import numpy as np
-
 sys.path.insert(0, ".")
 import lightworks_b200 as lb  # noqa: E402
 from lightworks_b200.convolution import pdist_calc  # noqa: E402

@@ -10,8 +10,6 @@ import itertools
 import sys
 import time
 
-import numpy as np
-
 sys.path.insert(0, ".")
 import lightworks_b200 as lb  # noqa: E402
 from lightworks_b200.convolution import pdist_calc  # noqa: E402

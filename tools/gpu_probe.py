@@ -2,7 +2,6 @@
 Run on the GPU box:  python tools/gpu_probe.py > gpurun_out/probe.log"""
 import json
 import sys
-import time
 
 import numpy as np
 import torch
