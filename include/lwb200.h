@@ -56,7 +56,9 @@ int lwb_device_info(lwb_handle h, int* sm_count, int* sm_clock_khz, char* name, 
 int lwb_set_tuning(int n, int log_l);
 /* Process-wide options.  "multiplicity_aware" (default 1): full-basis probability ranges use the
  * multiplicity-aware Glynn walk (prod(s_i+1)/2 terms for an output with occupations s_i) instead of
- * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel. */
+ * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel.
+ * "source_string_keys" (default 0, test hook): lwb_source_statistics keys its classes by strings even when the
+ * packed 62-bit form fits. */
 int lwb_set_option(const char* name, int value);
 /* Host-only view of the multiplicity-aware walk for n photons (2 <= n <= 16): pattern = index of a partition of
  * n (descending lexicographic order); returns its multiplicities (n_distinct entries, descending), the number of

@@ -35,6 +35,7 @@ static int fail(int code, const char* fmt, ...) {
 }
 namespace lwb {
 int set_error(int code, const char* msg) { return fail(code, "%s", msg); }  // for the host-only units (source_stats.cpp)
+int g_source_string_keys = 0;  // lwb_set_option("source_string_keys", 1): force the string-key path of lwb_source_statistics
 }  // namespace lwb
 #define CU(call)                                                                                 \
     do {                                                                                         \
@@ -226,6 +227,7 @@ int lwb_set_tuning(int n, int log_l) {
 int lwb_set_option(const char* name, int value) {
     if (!name) return fail(LWB_E_ARG, "null option name");
     if (!strcmp(name, "multiplicity_aware")) { g_multiplicity_aware = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "source_string_keys")) { lwb::g_source_string_keys = value ? 1 : 0; return 0; }
     return fail(LWB_E_ARG, "unknown option %s", name);
 }
 

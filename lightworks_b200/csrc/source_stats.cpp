@@ -23,6 +23,7 @@
 
 namespace lwb {
 int set_error(int code, const char* msg);  // lwb_api.cu: message for lwb_last_error()
+extern int g_source_string_keys;           // test hook: take the string-key path even when the packed form fits
 }
 
 namespace {
@@ -107,40 +108,98 @@ extern "C" int lwb_source_statistics(int n_modes, const uint8_t* state, double p
     }
     if (combos > 67108864.0) return lwb::set_error(LWB_E_LIMIT, "more than 2^26 input classes");
 
-    // product over modes (mode 0 outermost), merged in first-occurrence order
-    std::vector<std::string> keys;
+    // product over modes (mode 0 outermost, as the reference nests its loops), merged in first-occurrence order.
+    // Only occupied modes take part (an empty mode has the single class (0, 0, 1)); a class tuple is packed into one
+    // integer, (a_j + (c_j + 1) * b_j) in mixed radix, when that fits 62 bits (strings otherwise), and the running
+    // product / key / label-0 count are kept per odometer position so a step recomputes only the changed suffix.
+    std::vector<int> active;
+    for (int j = 0; j < n_modes; ++j)
+        if (state[j] > 0) active.push_back(j);
+    const int K = (int)active.size();
+    std::vector<uint64_t> stride(K + 1, 1), radix_a(K, 1);
+    bool packed = !lwb::g_source_string_keys;
+    for (int k = 0; packed && k < K; ++k) {
+        const uint64_t c = state[active[k]];
+        radix_a[k] = c + 1;
+        const uint64_t r = (c + 1) * (2 * c + 2);
+        if (stride[k] > (1ull << 62) / r) { packed = false; break; }
+        stride[k + 1] = stride[k] * r;
+    }
+    std::vector<std::string> keys;  // string form of every kept key (decoded from the integer form at the end)
+    std::vector<uint64_t> ikeys;
     std::vector<double> vals;
-    std::unordered_map<std::string, size_t> index;
-    std::vector<size_t> it(n_modes, 0);
-    std::string key(2 * (size_t)n_modes, '\0');
-    bool any_photon = false;
-    for (int j = 0; j < n_modes; ++j) any_photon |= state[j] > 0;
-    for (bool done = !any_photon && basic; !done;) {
-        double p = 1.0;
-        int total_a = 0, lone = -1;
-        for (int j = 0; j < n_modes; ++j) {
-            const ModeClass& m = per_mode[j][it[j]];
-            p *= m.p;
-            key[j] = (char)m.a;
-            key[n_modes + j] = (char)m.b;
-            total_a += m.a;
-            if (m.a) lone = j;
+    std::unordered_map<std::string, size_t> sindex;
+    std::unordered_map<uint64_t, size_t> iindex;
+    if (!(K == 0 && basic)) {
+        std::vector<size_t> it(K, 0);
+        std::vector<double> pp(K + 1, 1.0);
+        std::vector<uint64_t> pk(K + 1, 0);
+        std::vector<int> pa(K + 1, 0), plone(K + 1, -1);
+        std::string skey(2 * (size_t)n_modes, '\0');
+        int from = 0;
+        for (;;) {
+            for (int k = from; k < K; ++k) {
+                const ModeClass& m = per_mode[active[k]][it[k]];
+                pp[k + 1] = pp[k] * m.p;
+                pa[k + 1] = pa[k] + m.a;
+                plone[k + 1] = m.a ? k : plone[k];
+                if (packed) pk[k + 1] = pk[k] + ((uint64_t)m.a + radix_a[k] * (uint64_t)m.b) * stride[k];
+            }
+            const double p = pp[K];
+            // a lone label-0 photon is a distinguishable photon after relabelling (:262-283)
+            const bool lone = !basic && pa[K] == 1;
+            if (packed) {
+                uint64_t key = pk[K];
+                if (lone) key += (radix_a[plone[K]] - 1) * stride[plone[K]];  // a: 1 -> 0, b: +1
+                auto f = iindex.find(key);
+                if (f == iindex.end()) {
+                    iindex.emplace(key, vals.size());
+                    ikeys.push_back(key);
+                    vals.push_back(p);
+                } else {
+                    vals[f->second] += p;
+                }
+            } else {
+                std::fill(skey.begin(), skey.end(), '\0');
+                for (int k = 0; k < K; ++k) {
+                    const ModeClass& m = per_mode[active[k]][it[k]];
+                    skey[active[k]] = (char)m.a;
+                    skey[n_modes + active[k]] = (char)m.b;
+                }
+                if (lone) {
+                    const int j = active[plone[K]];
+                    skey[j] = 0;
+                    skey[n_modes + j] = (char)(skey[n_modes + j] + 1);
+                }
+                auto f = sindex.find(skey);
+                if (f == sindex.end()) {
+                    sindex.emplace(skey, vals.size());
+                    keys.push_back(skey);
+                    vals.push_back(p);
+                } else {
+                    vals[f->second] += p;
+                }
+            }
+            int k = K - 1;
+            while (k >= 0 && ++it[k] == per_mode[active[k]].size()) { it[k] = 0; --k; }
+            if (k < 0) break;
+            from = k;
         }
-        if (!basic && total_a == 1) {  // a lone label-0 photon is a distinguishable photon after relabelling (:262-283)
-            key[lone] = 0;
-            key[n_modes + lone] = (char)(key[n_modes + lone] + 1);
+        if (packed) {  // decode the integer keys
+            keys.resize(ikeys.size());
+            for (size_t i = 0; i < ikeys.size(); ++i) {
+                std::string sk(2 * (size_t)n_modes, '\0');
+                uint64_t key = ikeys[i];
+                for (int k = 0; k < K; ++k) {
+                    const uint64_t r = radix_a[k] * (2 * (radix_a[k] - 1) + 2);
+                    const uint64_t d = key % r;
+                    key /= r;
+                    sk[active[k]] = (char)(d % radix_a[k]);
+                    sk[n_modes + active[k]] = (char)(d / radix_a[k]);
+                }
+                keys[i] = sk;
+            }
         }
-        auto f = index.find(key);
-        if (f == index.end()) {
-            index.emplace(key, keys.size());
-            keys.push_back(key);
-            vals.push_back(p);
-        } else {
-            vals[f->second] += p;
-        }
-        int j = n_modes - 1;
-        while (j >= 0 && ++it[j] == per_mode[j].size()) { it[j] = 0; --j; }
-        done = j < 0;
     }
     if (keys.empty()) {  // source.py:221-223: an empty distribution returns the input itself
         std::string k(2 * (size_t)n_modes, '\0');

@@ -211,9 +211,14 @@ def test_source_statistics_match_reference(r):
     ann, got = O.py_build_statistics(r["state"], **kw)
     assert ann == r["annotated"] and list(got) == want_keys
     assert rel_close(list(got.values()), r["vals"], 1e-12)
-    ann2, entries = L.source_statistics(r["state"], **kw)
-    assert ann2 == r["annotated"] and [k for k, _ in entries] == want_keys
-    assert rel_close([p for _, p in entries], r["vals"], 1e-12)
+    for string_keys in (0, 1):  # packed integer keys, and the string-key path used when they would not fit 62 bits
+        L.set_option("source_string_keys", string_keys)
+        try:
+            ann2, entries = L.source_statistics(r["state"], **kw)
+        finally:
+            L.set_option("source_string_keys", 0)
+        assert ann2 == r["annotated"] and [k for k, _ in entries] == want_keys
+        assert rel_close([p for _, p in entries], r["vals"], 1e-12)
 
 
 def test_source_statistics_errors_and_scale():
