@@ -194,3 +194,24 @@ def test_reference_source_suite_with_native_statistics():
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, (r.stdout + r.stderr)[-2000:]
     assert " passed" in r.stdout
+
+
+@pytest.mark.reference
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's own CPU path, no GPU involved) prints one JSON line with the
+    contract keys; under torchrun only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--ref-sample", "200"]
+    r = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "higher_is_better", "cpu_baseline", "e2e", "config"):
+        assert key in line
+    assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
+    r1 = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
