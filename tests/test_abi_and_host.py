@@ -215,3 +215,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["impl"] == "reference" and line["value"] > 0 and line["e2e"]["h2d_bytes_per_step"] == 0
     r1 = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=600, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert r1.returncode == 0 and r1.stdout.strip() == ""
+
+
+def test_host_entry_points_reject_bad_arguments():
+    """Limits and argument errors of the host-only entry points come back as ValueError with a message, never as a
+    wrong answer (include/lwb200.h: LWB_E_ARG / LWB_E_LIMIT)."""
+    with pytest.raises(ValueError):
+        lb.fock_count(200, 3)  # > 128 modes
+    with pytest.raises(ValueError):
+        lb.fock_unrank(4, 2, lb.fock_count(4, 2))  # rank outside the space
+    with pytest.raises(ValueError):
+        _lib.keyspace_size(0, 2)
+    with pytest.raises(ValueError):
+        _lib.keyspace_states(3, 2, [_lib.keyspace_size(3, 2)])
+    with pytest.raises(ValueError):  # 5^12 label classes: beyond the 2^26 enumeration bound, refused up front
+        _lib.source_statistics([1] * 12, purity=0.9, brightness=0.9, indistinguishability=0.9)
+    with pytest.raises(ValueError):
+        _lib.set_option("no_such_option", 1)
+    assert "option" in _lib.cdll().lwb_last_error().decode()
+    # zero threshold keeps every class; the probabilities still sum to one
+    ann, entries = _lib.source_statistics([1, 1, 0], purity=0.8, brightness=0.7, indistinguishability=0.6,
+                                          probability_threshold=0.0)
+    assert ann and sum(p for _, p in entries) == pytest.approx(1.0, abs=1e-13)
+    assert len(entries) > len(_lib.source_statistics([1, 1, 0], purity=0.8, brightness=0.7, indistinguishability=0.6,
+                                                     probability_threshold=5e-2)[1])
