@@ -32,13 +32,37 @@ template <typename T> struct vec2;
 template <> struct vec2<double> { using type = double2; };
 template <> struct vec2<float> { using type = float2; };
 
+// Complex multiply-accumulate forms (all 2 mul + 2 fma; they differ in which operands the instruction pairs share,
+// i.e. in the operand-reuse hits ptxas can give the 3-operand DFMAs - see profiles/r02_fp64_reuse_study.md).
+#ifndef LWB_CMUL_FORM
+#define LWB_CMUL_FORM 0
+#endif
 template <typename T>
 __device__ __forceinline__ void cmul(T& pr, T& pi, T ar, T ai) {
-    // (pr + i pi) * (ar + i ai): 2 mul + 2 fma
+#if LWB_CMUL_FORM == 0
+    // (pr + i pi) * (ar + i ai): the mul pair shares pr, the fma pair shares pi
     T nr = pr * ar;
     T ni = pr * ai;
     nr = fma(-pi, ai, nr);
     ni = fma(pi, ar, ni);
+#elif LWB_CMUL_FORM == 1
+    // mul pair shares pi, fma pair shares pr
+    T t1 = pi * ai;
+    T t2 = pi * ar;
+    T nr = fma(pr, ar, -t1);
+    T ni = fma(pr, ai, t2);
+#elif LWB_CMUL_FORM == 2
+    // pairs share the FACTOR: (mul, fma) on ar, (mul, fma) on ai
+    T nr = pr * ar;
+    T ni = pi * ar;
+    nr = fma(-pi, ai, nr);
+    ni = fma(pr, ai, ni);
+#else
+    T ni = pr * ai;
+    T nr = pr * ar;
+    ni = fma(pi, ar, ni);
+    nr = fma(-pi, ai, nr);
+#endif
     pr = nr;
     pi = ni;
 }
@@ -49,11 +73,23 @@ __device__ __forceinline__ void cmul(T& pr, T& pi, T ar, T ai) {
 #endif
 template <int N, typename T>
 __device__ __forceinline__ void cprod(const T (&wr)[N], const T (&wi)[N], T& pr, T& pi) {
+#ifdef LWB_PROD_TREE
+    // pairwise tree: N-1 multiplies like the chains, depth ceil(log2 N)
+    T cr[N], ci[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { cr[j] = wr[j]; ci[j] = wi[j]; }
+#pragma unroll
+    for (int step = 1; step < N; step <<= 1) {
+#pragma unroll
+        for (int j = 0; j + step < N; j += 2 * step) cmul(cr[j], ci[j], cr[j + step], ci[j + step]);
+    }
+    pr = cr[0];
+    pi = ci[0];
+#else
     constexpr int K = (N >= 2 * LWB_CHAINS) ? LWB_CHAINS : 1;
     T cr[K], ci[K];
 #pragma unroll
     for (int c = 0; c < K; ++c) {
-        constexpr int dummy = 0; (void)dummy;
         const int lo = (N * c) / K, hi = (N * (c + 1)) / K;
         cr[c] = wr[lo];
         ci[c] = wi[lo];
@@ -64,6 +100,7 @@ __device__ __forceinline__ void cprod(const T (&wr)[N], const T (&wi)[N], T& pr,
     for (int c = 1; c < K; ++c) cmul(cr[0], ci[0], cr[c], ci[c]);
     pr = cr[0];
     pi = ci[0];
+#endif
 }
 
 // Shared-memory row reads go through volatile inline PTX: the row table is loop-invariant, and

@@ -38,6 +38,28 @@ struct K1Shape {
     static constexpr int GPB = K1_THREADS / L;       // groups (permanents in flight) per block
 };
 
+// complex64 drift control.  The incrementally updated column sums w_j pick up a rounding error that grows like
+// sqrt(steps) * eps * n; for float (eps 6e-8) a 2^14-step chunk would leave ~1.5e-4, above the 1e-4 the complex64
+// variant promises.  A float lane therefore restarts from a freshly derived start vector every 2^LWB_F32_RESTART steps
+// (cost: n^2 FMAs per restart, ~1 % at 2^9) and adds the sub-chunk sums in double.  Double keeps one start per chunk.
+#ifndef LWB_F32_RESTART
+#define LWB_F32_RESTART 9
+#endif
+template <int N, int C, int U, typename T>
+__device__ __forceinline__ void glynn_chunk_acc(const typename vec2<T>::type* __restrict__ rows,
+                                                const int* __restrict__ rowidx, uint32_t q, double& dr, double& di) {
+    constexpr bool SPLIT = sizeof(T) == 4 && C > LWB_F32_RESTART;
+    constexpr int R = SPLIT ? LWB_F32_RESTART : C;
+    constexpr int UR = U < R ? U : R;
+#pragma unroll 1
+    for (uint32_t i = 0; i < (1u << (C - R)); ++i) {
+        T sr = T(0), si = T(0);
+        glynn_chunk<N, R, UR, T>(rows, rowidx, (q << (C - R)) + i, sr, si);
+        dr += (double)sr;
+        di += (double)si;
+    }
+}
+
 struct PermStatesArgs {
     const double2* U;          // m x m complex128, row-major, device
     int m;
@@ -129,10 +151,10 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
 
     for (uint64_t it = 0; it < max_len; ++it) {
         const bool active = it < my_len;
-        T sr = T(0), si = T(0);
-        glynn_chunk<N, S::C, S::U, T>(Vs, rowidx, (uint32_t)lane_g, sr, si);
-        double dr = group_sum<double>((double)sr, LOG_L);
-        double di = group_sum<double>((double)si, LOG_L);
+        double dr = 0.0, di = 0.0;
+        glynn_chunk_acc<N, S::C, S::U, T>(Vs, rowidx, (uint32_t)lane_g, dr, di);
+        dr = group_sum<double>(dr, LOG_L);
+        di = group_sum<double>(di, LOG_L);
         __syncwarp();
         if (lane_g == 0 && active) {
             if (!a.out_states) {  // factorials of the current occupation (runs of equal modes)
@@ -218,10 +240,10 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_matrices_kernel(Per
             for (int e = lane_g; e < N * N; e += S::L) { V v; v.x = T(0); v.y = T(0); Ms[e] = v; }
         }
         __syncwarp();
-        T sr = T(0), si = T(0);
-        glynn_chunk<N, S::C, S::U, T>(Ms, ident, (uint32_t)lane_g, sr, si);
-        double dr = group_sum<double>((double)sr, LOG_L);
-        double di = group_sum<double>((double)si, LOG_L);
+        double dr = 0.0, di = 0.0;
+        glynn_chunk_acc<N, S::C, S::U, T>(Ms, ident, (uint32_t)lane_g, dr, di);
+        dr = group_sum<double>(dr, LOG_L);
+        di = group_sum<double>(di, LOG_L);
         if (lane_g == 0 && active) {
             a.out[2 * b] = 2.0 * dr;
             a.out[2 * b + 1] = 2.0 * di;
@@ -273,10 +295,15 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermS
         const uint64_t total = a.q_end - a.q_begin;
         const uint64_t b = a.q_begin + (total / lanes) * lane + (lane < total % lanes ? lane : total % lanes);
         const uint64_t cnt = total / lanes + (lane < total % lanes ? 1 : 0);
-        T sr = T(0), si = T(0);
-        glynn_range<N, S::C, S::U, T>(Ms, ident, b, cnt, sr, si);
-        dr = (double)sr;
-        di = (double)si;
+        // complex64: restart from a fresh start vector every 2^LWB_F32_RESTART steps (drift control, see glynn_chunk_acc)
+        constexpr uint64_t PIECE = sizeof(T) == 4 ? (1ull << (LWB_F32_RESTART > S::C ? LWB_F32_RESTART - S::C : 0)) : ~0ull;
+#pragma unroll 1
+        for (uint64_t done = 0; done < cnt; done += PIECE) {
+            T sr = T(0), si = T(0);
+            glynn_range<N, S::C, S::U, T>(Ms, ident, b + done, (cnt - done < PIECE) ? cnt - done : PIECE, sr, si);
+            dr += (double)sr;
+            di += (double)si;
+        }
     }
     __syncwarp();
     dr = group_sum<double>(dr, 5);

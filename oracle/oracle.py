@@ -46,6 +46,8 @@ def lib():
         L.lwo_fock_basis.argtypes = [C.c_int, C.c_int, vp, C.c_uint64]
         L.lwo_perm.restype = None
         L.lwo_perm.argtypes = [vp, C.c_int, vp]
+        L.lwo_perm_hp.restype = None
+        L.lwo_perm_hp.argtypes = [vp, C.c_int, vp, C.c_int]
         L.lwo_perm_batch.restype = None
         L.lwo_perm_batch.argtypes = [vp, C.c_int, C.c_int, vp]
         L.lwo_perm_batch_mt.restype = None
@@ -252,6 +254,16 @@ def perm(A) -> complex:  # noqa: N803
     A = _c128(A)  # noqa: N806
     out = np.zeros(2)
     lib().lwo_perm(_p(A), A.shape[0], _p(out))
+    return complex(out[0], out[1])
+
+
+def perm_hp(A, threads: int | None = None) -> complex:  # noqa: N803
+    """Extended-precision ADJUDICATOR (lw_oracle.c lwo_perm_hp): the same Glynn sum in long double with compensated
+    accumulation.  Not a restatement of the reference: the yardstick that tells which side of a mismatch at n >= 20
+    carries the rounding error (the reference's incremental double-precision loop does)."""
+    A = _c128(A)  # noqa: N806
+    out = np.zeros(2)
+    lib().lwo_perm_hp(_p(A), A.shape[0], _p(out), threads or (os.cpu_count() or 1))
     return complex(out[0], out[1])
 
 
