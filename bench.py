@@ -259,7 +259,7 @@ def main() -> int:  # noqa: PLR0915
     import torch.distributed as dist
 
     import lightworks_b200 as lb
-    from lightworks_b200 import _lib, sharding
+    from lightworks_b200 import _lib
     O = _Inputs  # noqa: N806  Haar inputs; oracle/ is only imported by the cpu_baseline and --impl reference legs
 
     rank = int(os.environ.get("RANK", "0"))
@@ -279,15 +279,21 @@ def main() -> int:  # noqa: PLR0915
     U = O.random_unitary(M, SEED)  # noqa: N806  == lw.random_unitary(24, seed=3) (sdk/utils/random.py:66-67)
     ins = np.array([1] * N_PH + [0] * (M - N_PH), dtype=np.uint8)
     S = lb.fock_count(M, N_PH)  # noqa: N806
-    # contiguous rank-range shards; boundaries equalise the WORK of the multiplicity-aware walk (early ranks bunch more)
-    # (exact cumulative-work bisection on the host, lightworks_b200/sharding.py)
-    # Pieces of decreasing work: the all-gather of a piece overlaps the kernels of the next one, so only the small last
-    # piece's exchange is exposed (8 GPUs: 1 piece 15.2 ms, 2 equal 14.2, 4 equal 14.4 per step).
-    fractions = [float(x) for x in os.environ.get("LWB_BENCH_PIECES", "0.6,0.3,0.1").split(",")] if world > 1 else [1.0]
-    SUB = len(fractions)  # noqa: N806
-    pieces = sharding.work_balanced_ranges(M, N_PH, world, fractions)
-    shard_ranges = [(pieces[r][0][0], pieces[r][-1][1]) for r in range(world)]
-    r0, r1 = shard_ranges[rank]
+    # N > 1: the PRODUCT's multi-GPU entry point (include/lwb200.h "multi-GPU", lightworks_b200.Comm): contiguous
+    # rank-range shards of equal WORK (lwb_shard_cuts), every probability stored straight into the peers' copies of the
+    # distribution by the permanent kernel (NVLink peer stores, CUDA IPC between the ranks), one all-reduce of the sum
+    # that doubles as the completion barrier.  Every rank ends each step with the WHOLE distribution, contiguous, in
+    # fock_basis order.  bench.py only broadcasts the NCCL unique id and times the call.
+    comm = None
+    if world > 1:
+        uid = [lb.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = lb.Comm.rank(ctx, rank, world, uid[0])
+        if os.environ.get("LWB_BENCH_PEER_STORES"):
+            comm.set_option("peer_stores", int(os.environ["LWB_BENCH_PEER_STORES"]))
+        r0, r1 = comm.shard(M, N_PH, rank)
+    else:
+        r0, r1 = 0, S
     cnt = r1 - r0
 
     def barrier():
@@ -295,50 +301,33 @@ def main() -> int:  # noqa: PLR0915
             dist.barrier()
         torch.cuda.synchronize()
 
-    # Every shard is cut into SUB pieces; the all-gather of piece j (NCCL, side stream) overlaps the kernel of
-    # piece j+1.  Pieces have unequal lengths across ranks (equal work), so every rank writes its piece at the head of
-    # a max-length slot and ONE ncclAllGather per piece moves the slots; the distribution on every rank is the ragged
-    # view  d_full[j].view(world, slot_j)[r, :len(piece j of rank r)]  (padding stays zero).
-    slot_len = [max(pieces[r][j][1] - pieces[r][j][0] for r in range(world)) for j in range(SUB)]
     with torch.cuda.stream(stream):
         d_U = torch.from_numpy(U).cuda()  # noqa: N806  resident inputs for the device-timed region
         d_ins = torch.from_numpy(ins).cuda()
-        d_slot = [torch.zeros(slot_len[j], dtype=torch.float64, device="cuda") for j in range(SUB)]
-        d_full = [torch.zeros(world * slot_len[j], dtype=torch.float64, device="cuda") for j in range(SUB)] if world > 1 else None
-        d_sum = torch.zeros(1, dtype=torch.float64, device="cuda")
+        d_probs = torch.zeros(cnt, dtype=torch.float64, device="cuda")  # this rank's shard (N = 1: everything)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    d_probs = d_slot[0][:cnt] if SUB == 1 else None
-    comm_stream = torch.cuda.Stream() if world > 1 else None
+    comm_out = {}
 
     def device_step():
         if world == 1:
             ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
-            return
-        works = []
-        d_sum.zero_()
-        for j in range(SUB):
-            a, b = pieces[rank][j]
-            ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, a, b - a, d_slot[j])
-            d_sum.add_(d_slot[j].sum())
-            comm_stream.wait_stream(stream)
-            with torch.cuda.stream(comm_stream):
-                works.append(dist.all_gather_into_tensor(d_full[j], d_slot[j], async_op=True))
-        with torch.cuda.stream(comm_stream):
-            works.append(dist.all_reduce(d_sum, async_op=True))
-        for w in works:
-            w.wait()
-        stream.wait_stream(comm_stream)
+        else:
+            comm_out["probs"], comm_out["sum"] = comm.perm_basis_probs_dev(d_U, M, d_ins, N_PH)
 
     # pinned host buffers for the end-to-end leg
     h_U = torch.from_numpy(U.copy()).pin_memory()  # noqa: N806
     h_ins = torch.from_numpy(ins.copy()).pin_memory()
-    h_out = torch.empty(cnt, dtype=torch.float64).pin_memory()
+    h_out = torch.empty(S if world > 1 else cnt, dtype=torch.float64).pin_memory()
     h_U_np, h_ins_np, h_out_np = h_U.numpy(), h_ins.numpy(), h_out.numpy()  # noqa: N806
 
     def e2e_step():
-        # the public host-buffer API: H2D of U + input, kernel, D2H of this rank's probabilities, sync
-        # (every rank ends with its rank-range shard in its own host buffer; no host-side reduction)
-        ctx.perm_basis_probs(h_U_np, h_ins_np, r0, cnt, out=h_out_np)
+        # the public host-buffer API: H2D of U + input, kernels (N > 1: incl. the peer-store exchange and the
+        # all-reduce, so every rank's DEVICE copy is complete), D2H of this rank's shard into its slice of the host
+        # array, sync.  (N > 1: one process per GPU - each rank's host holds its own rank range.)
+        if world == 1:
+            ctx.perm_basis_probs(h_U_np, h_ins_np, r0, cnt, out=h_out_np)
+        else:
+            comm.perm_basis_probs(h_U_np, h_ins_np, gather_host=False, out=h_out_np)
 
     def timed(step_fn, k, sampler=None):
         """K steps between barrier+synchronize; per-step CUDA events on the launch stream; the L2 flush
@@ -379,15 +368,15 @@ def main() -> int:  # noqa: PLR0915
     launches = ctx.launch_count() - l0
     per_rank_ms = None
     if world > 1:
-        # balance diagnostic: every rank's own shard kernels WITHOUT the collectives (3 repetitions, best)
+        # balance diagnostic: every rank's own shard kernels WITHOUT peer stores or collectives (3 repetitions, best)
         best = 1e30
         with torch.cuda.stream(stream):
+            ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)  # warm: sizes the scratch for this shard
+            stream.synchronize()
             for _ in range(3):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-                for j in range(SUB):
-                    a, b = pieces[rank][j]
-                    ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, a, b - a, d_slot[j])
+                ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)
                 e1.record(stream)
                 e1.synchronize()
                 best = min(best, e0.elapsed_time(e1))
@@ -396,10 +385,17 @@ def main() -> int:  # noqa: PLR0915
         dist.all_reduce(t_all)
         per_rank_ms = [round(float(v), 3) for v in t_all]
     dev_ms = max_over_ranks(dev_ms)
-    total_sum = float(d_probs.sum()) if world == 1 else float(d_sum)
-    if world > 1:
-        gathered = sum(float(t.sum()) for t in d_full)
-        assert abs(gathered - total_sum) < 1e-9, (gathered, total_sum)  # every rank holds the whole distribution
+    if world == 1:
+        total_sum = float(d_probs.sum())
+    else:
+        # every rank holds the whole distribution, contiguous: its own shard bit-identical to the stand-alone launch,
+        # the sum of the complete copy equal to the all-reduced sum of the shard sums
+        full = torch.as_tensor(comm_out["probs"], device="cuda")
+        total_sum = float(torch.as_tensor(comm_out["sum"], device="cuda")[0])
+        assert full.numel() == S
+        assert torch.equal(full[r0:r1], d_probs), "sharded result differs from the stand-alone shard"
+        assert abs(float(full.sum()) - total_sum) < 1e-9, (float(full.sum()), total_sum)
+        assert abs(total_sum - 1.0) < 1e-9, total_sum
     value = S * args.steps / (dev_ms * 1e-3)
 
     # ---- end-to-end through the host-buffer C ABI ----
@@ -420,12 +416,10 @@ def main() -> int:  # noqa: PLR0915
     # `executed_frac` counts the FP64 work K1x really issues (terms x (8n-2)).
     peak = ctx.fp64_peak()  # measured live: MEASURED_PEAKS.json carries no FP64 entry
 
-    if d_probs is None:
-        with torch.cuda.stream(stream):
-            d_probs = torch.empty(cnt, dtype=torch.float64, device="cuda")
-
     def kernel_ms(reps=3):
         with torch.cuda.stream(stream):
+            ctx.perm_basis_probs_dev(d_U, M, d_ins, N_PH, r0, cnt, d_probs)  # warm-up: scratch sized, caches primed
+            stream.synchronize()
             kev = []
             for _ in range(reps):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -481,37 +475,51 @@ def main() -> int:  # noqa: PLR0915
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "c128", "data": "synthetic",
         "config": {"workload": WORKLOAD, "modes": M, "photons": N_PH, "outputs": S,
-                   "parallelism": f"fock-rank-range shards x{world} (equal work)" + (f" in {SUB} pieces, NCCL all-gather of piece j overlapped with the kernel of piece j+1, all-reduce of the sum" if world > 1 else ""),
+                   "parallelism": f"fock-rank-range shards x{world} (equal work)" + (
+                       f", lwb_comm_perm_basis_probs_dev: {'in-kernel NVLink peer stores into every rank' if comm.info()['peer_stores'] else 'in-place NCCL broadcasts of the shards'}"
+                       " + NCCL all-reduce of the sum; every rank ends with the whole contiguous distribution" if world > 1 else ""),
                    "l2": "256 MiB flush between timed steps (outside the event pairs); outputs 740 MB > 126 MB L2",
                    "check_sum_of_probabilities": total_sum},
         "roofline": roofline, "roofline_expanded_rows": roofline_plain,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(U.nbytes + ins.nbytes),
                 "d2h_bytes_per_step": int(cnt * 8), "ms_per_step": 1e3 * e2e_s / args.steps,
-                "api": "lwb_perm_basis_probs (host buffers, pinned) via lightworks_b200.Context.perm_basis_probs"},
+                "api": ("lwb_perm_basis_probs (host buffers, pinned) via lightworks_b200.Context.perm_basis_probs" if world == 1 else
+                        "lwb_comm_perm_basis_probs (host buffers, pinned; device copies complete on every rank, each rank "
+                        "copies its own rank range to its host) via lightworks_b200.Comm.perm_basis_probs")},
         "gpu_launches": int(launches), "clocks": clocks, "wall_ms_timed_region": dev_wall,
     }
     if per_rank_ms is not None:
         line["per_rank_compute_ms"] = per_rank_ms  # shard kernels only, no collectives
 
     if world > 1 and not args.no_extras:
-        # C5: one 28 x 28 permanent of the 60-mode Haar unitary (seed 5), Gray-code space sliced over the ranks,
-        # partial sums combined by a 16-byte all-reduce
-        n5 = 28
-        with torch.cuda.stream(stream):
-            A5 = torch.from_numpy(O.random_unitary(60, 5)[:n5, :n5].copy()).cuda()  # noqa: N806
-            o5 = torch.zeros(2, dtype=torch.float64, device="cuda")
+        # C5: single n x n permanents of the 60-mode Haar unitary (seed 5), Gray-code space sliced over the ranks by
+        # lwb_comm_perm_single_dev (16-byte NCCL all-reduce inside the call); the same permanent on ONE GPU beside it
+        U60 = O.random_unitary(60, 5)  # noqa: N806
+        c5 = {}
+        for n5 in (20, 22, 24, 26, 28):
+            with torch.cuda.stream(stream):
+                A5 = torch.from_numpy(U60[:n5, :n5].copy()).cuda()  # noqa: N806
+                o5 = torch.zeros(2, dtype=torch.float64, device="cuda")
+                o1 = torch.zeros(2, dtype=torch.float64, device="cuda")
 
-        def single_step():
-            ctx.perm_single_dev(A5, n5, o5, slice_=rank, n_slices=world)
-            dist.all_reduce(o5)
+            def single_step():
+                comm.perm_single_dev(A5, n5, o5)
 
-        with torch.cuda.stream(stream):
-            single_step()
-        ms5, _, _ = timed(single_step, 5)
-        ms5 = max_over_ranks(ms5) / 5
-        line["extra"] = {"single_perm_n28_sharded": {"ms": ms5, "permanents_per_s": 1e3 / ms5,
-                                                      "fp64_frac_per_gpu": flops_per_perm(n5) / (ms5 * 1e-3) / peak / world,
-                                                      "value": [float(o5[0]), float(o5[1])]}}
+            def single_one_gpu():
+                ctx.perm_single_dev(A5, n5, o1)
+
+            with torch.cuda.stream(stream):
+                single_step()
+                single_one_gpu()
+            ms5, _, _ = timed(single_step, 5)
+            ms5 = max_over_ranks(ms5) / 5
+            ms1, _, _ = timed(single_one_gpu, 5)
+            ms1 = max_over_ranks(ms1) / 5
+            assert abs(complex(float(o5[0]), float(o5[1])) - complex(float(o1[0]), float(o1[1]))) <= 1e-10 * abs(complex(float(o1[0]), float(o1[1])))
+            c5[f"n{n5}"] = {"ms": ms5, "ms_one_gpu": ms1, "speedup": ms1 / ms5, "efficiency": ms1 / ms5 / world,
+                            "permanents_per_s": 1e3 / ms5,
+                            "fp64_frac_per_gpu": flops_per_perm(n5) / (ms5 * 1e-3) / peak / world}
+        line["extra"] = {"single_perm_sharded": c5}
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1
         line["cpu_baseline"] = cpu_port_baseline(U, ins, args.cpu_sample, threads)
@@ -523,6 +531,8 @@ def main() -> int:  # noqa: PLR0915
     if rank == 0:
         emit(line)
     if world > 1:
+        barrier()
+        comm.close()  # collective: every rank unmaps its peers before anybody frees
         dist.destroy_process_group()
     return 0
 

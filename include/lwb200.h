@@ -37,7 +37,8 @@ enum {
     LWB_E_PHOTONS = -2,  /* photon-number mismatch (PhotonNumberError / ValueError)  */
     LWB_E_LIMIT = -3,    /* size beyond what the kernels are built for              */
     LWB_E_CUDA = -4,     /* CUDA runtime error (BackendError)                       */
-    LWB_E_NOMEM = -5
+    LWB_E_NOMEM = -5,
+    LWB_E_COMM = -6      /* NCCL missing or a collective failed (BackendError)        */
 };
 
 /* ---- lifecycle ---------------------------------------------------------------------------- */
@@ -188,6 +189,59 @@ int lwb_dist_free(lwb_handle h, int slot);
 int lwb_source_statistics(int n_modes, const uint8_t* state, double purity, double brightness,
                           double indistinguishability, double threshold, uint64_t cap, uint8_t* group_occ,
                           uint8_t* single_occ, double* probs, uint64_t* count, int* annotated);
+
+/* ---- multi-GPU (SURVEY.md section 8b "lwb_init(n_gpus)", 8e) --------------------------------------------
+ * The path shards where the reference loops over independent units: output Fock states of one distribution
+ * (permanent.py:145-157), the Gray-code space of one large permanent (thewalrus.perm, call site permanent.py:81),
+ * and the unique sub-inputs of an imperfect source (probability_distribution.py:127-133).  A communicator is
+ *   LOCAL: one process drives n GPUs - lwb_comm_init_local(n_gpus) creates one handle per device (this is SURVEY
+ *          8b's lwb_init(n_gpus)); what lightworks_b200.install(n_gpus=N) puts behind Backend("permanent"); or
+ *   RANK:  one process per GPU - lwb_comm_init_rank(handle, rank, world, id) with the 128-byte NCCL unique id from
+ *          lwb_comm_unique_id() on rank 0, broadcast by the host framework (torchrun, MPI, a file).
+ * NCCL is dlopen'ed ("libnccl.so.2"): no link-time dependency, shares the NCCL the host process already loaded.
+ * Shards of a distribution are contiguous rank ranges of fock_basis(m, n) holding equal WORK of the
+ * multiplicity-aware walk (lwb_shard_cuts).  When the GPUs can map each other's memory (NVLink peer access, CUDA IPC
+ * between processes) the permanent kernels store every probability into the peers' copies as it is produced and the
+ * step ends with the all-reduce of the sum, which doubles as the completion barrier; otherwise the shards travel by
+ * in-place NCCL broadcasts.  Every rank (LOCAL: device 0) ends with the WHOLE distribution, contiguous, in
+ * fock_basis order. */
+typedef struct lwb_comm_s* lwb_comm;
+int lwb_comm_unique_id(uint8_t* id128);
+int lwb_comm_init_rank(lwb_handle h, int rank, int world, const uint8_t* id128, lwb_comm* out);
+int lwb_comm_init_local(int n_gpus, lwb_comm* out);
+int lwb_comm_destroy(lwb_comm c);
+/* kind: 0 LOCAL, 1 RANK; peer_stores: 1 when kernels write into the peers' buffers directly */
+int lwb_comm_info(lwb_comm c, int* rank, int* world, int* kind, int* peer_stores);
+/* "peer_stores" 0/1: force the NCCL-broadcast (RANK) / peer-copy (LOCAL) exchange instead of in-kernel peer stores */
+int lwb_comm_set_option(lwb_comm c, const char* name, int value);
+/* LOCAL: the handle of device `index` (owned by the communicator); RANK: index 0 = the caller's handle */
+int lwb_comm_handle(lwb_comm c, int index, lwb_handle* out);
+/* Ranks of fock_basis(m, n) at which the cumulative work of the permanent walk reaches the given ascending
+ * fractions in [0, 1] (host, exact integer arithmetic; n < 7 or n > 16: uniform cost per state). */
+int lwb_shard_cuts(int m, int n, int n_fractions, const double* fractions, uint64_t* cuts);
+int lwb_comm_shard(lwb_comm c, int m, int n, int rank, uint64_t* r0, uint64_t* r1);
+/* lwb_perm_basis_probs over the whole basis, sharded.  probs may be NULL (result stays on the device).
+ *   LOCAL: probs receives all S probabilities.  RANK: all S when gather_host != 0, else only this rank's shard,
+ *   written at probs + r0 (every rank's DEVICE copy is complete either way).  sum_out: sum of all probabilities. */
+int lwb_comm_perm_basis_probs(lwb_comm c, const double* U, int m, const uint8_t* in_state, int dtype, int gather_host,
+                              double* probs, double* sum_out);
+/* RANK only, device-resident inputs of this rank, asynchronous on the handle's stream: *d_probs = this rank's
+ * complete copy (library-owned, S doubles), *d_sum = device scalar holding the all-reduced sum. */
+int lwb_comm_perm_basis_probs_dev(lwb_comm c, const double* d_U, int m, const uint8_t* d_in_state, int n_photons,
+                                  int dtype, double** d_probs, double** d_sum);
+/* lwb_pdist(backend = permanent) with the permanents sharded over the communicator. */
+int lwb_comm_pdist(lwb_comm c, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state, double threshold,
+                   int dtype, uint8_t* keys, double* vals, uint64_t cap, uint64_t* count_out);
+/* lwb_perm_single with the Gray-code space split over the communicator and the 16-byte sum (NCCL all-reduce for
+ * RANK, fixed-order host sum for LOCAL). */
+int lwb_comm_perm_single(lwb_comm c, const double* A, int n, int dtype, double* out2);
+int lwb_comm_perm_single_dev(lwb_comm c, const double* d_A, int n, int dtype, double* d_out2);
+/* lwb_dist_from_circuit for `count` input states at once (probability_distribution.py:127-133: the unique
+ * sub-inputs of an imperfect source).  h: the handle that receives the slots.  comm may be NULL (everything on h,
+ * one synchronisation at the end) or a LOCAL communicator whose device 0 is h: input k is computed on device
+ * k mod n_gpus and its dense distribution copied to h's device over NVLink. */
+int lwb_dists_from_circuit(lwb_handle h, lwb_comm comm, const double* U_full, int m_tot, int n_modes,
+                           const uint8_t* in_states, int count, double threshold, int backend, int dtype, int* slots);
 
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */

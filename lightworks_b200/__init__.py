@@ -10,6 +10,7 @@ from ._lib import (  # noqa: F401
     LWB_C64,
     LWB_C128,
     BackendError,
+    Comm,
     Context,
     PhotonNumberError,
     DeviceDistribution,
@@ -19,6 +20,7 @@ from ._lib import (  # noqa: F401
     fock_unrank,
     set_option,
     set_tuning,
+    shard_cuts,
     slos_rank,
     slos_unrank,
     source_statistics,
@@ -31,6 +33,7 @@ from .backends import (  # noqa: E402, F401
     SLOSBackend,
     install,
     set_convolve_on_gpu,
+    set_n_gpus,
     set_native_source_statistics,
     uninstall,
 )

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LWB_LIB_PATH") or os.path.join(_HERE, "liblwb200.so")  # override: experiment builds
 
 LWB_C128, LWB_C64 = 0, 1
-LWB_E_ARG, LWB_E_PHOTONS, LWB_E_LIMIT, LWB_E_CUDA, LWB_E_NOMEM = -1, -2, -3, -4, -5
+LWB_E_ARG, LWB_E_PHOTONS, LWB_E_LIMIT, LWB_E_CUDA, LWB_E_NOMEM, LWB_E_COMM = -1, -2, -3, -4, -5, -6
 
 
 class BackendError(Exception):
@@ -82,6 +82,21 @@ SIGNATURES = {
     "lwb_dist_sample": (_i, [_vp, _i, _vp, _u64, _vp, _pdbl]),
     "lwb_dist_free": (_i, [_vp, _i]),
     "lwb_source_statistics": (_i, [_i, _vp, _dbl, _dbl, _dbl, _dbl, _u64, _vp, _vp, _vp, _pu64, _pi]),
+    "lwb_comm_unique_id": (_i, [_vp]),
+    "lwb_comm_init_rank": (_i, [_vp, _i, _i, _vp, C.POINTER(_vp)]),
+    "lwb_comm_init_local": (_i, [_i, C.POINTER(_vp)]),
+    "lwb_comm_destroy": (_i, [_vp]),
+    "lwb_comm_info": (_i, [_vp, _pi, _pi, _pi, _pi]),
+    "lwb_comm_set_option": (_i, [_vp, C.c_char_p, _i]),
+    "lwb_comm_handle": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "lwb_shard_cuts": (_i, [_i, _i, _i, _vp, _vp]),
+    "lwb_comm_shard": (_i, [_vp, _i, _i, _i, _pu64, _pu64]),
+    "lwb_comm_perm_basis_probs": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _pdbl]),
+    "lwb_comm_perm_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _i, C.POINTER(_vp), C.POINTER(_vp)]),
+    "lwb_comm_pdist": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _vp, _vp, _u64, _pu64]),
+    "lwb_comm_perm_single": (_i, [_vp, _vp, _i, _i, _vp]),
+    "lwb_comm_perm_single_dev": (_i, [_vp, _vp, _i, _i, _vp]),
+    "lwb_dists_from_circuit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _dbl, _i, _i, _vp]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
     "lwb_fp64_probe": (_i, [_vp, _i, _pdbl]),
 }
@@ -300,15 +315,19 @@ class DeviceDistribution:
 class Context:
     """One lwb_handle (one GPU).  Thin, typed wrappers over the C ABI with numpy host buffers."""
 
-    def __init__(self, device: int = 0):
-        self._h = C.c_void_p(0)
-        check(cdll().lwb_create(device, C.byref(self._h)))
+    def __init__(self, device: int = 0, _borrowed=None):
+        self._owned = _borrowed is None
+        if _borrowed is not None:  # a handle owned by a communicator (lwb_comm_handle)
+            self._h = _borrowed
+        else:
+            self._h = C.c_void_p(0)
+            check(cdll().lwb_create(device, C.byref(self._h)))
         self.device = device
 
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             cdll().lwb_destroy(self._h)
-            self._h = C.c_void_p(0)
+        self._h = C.c_void_p(0)
 
     def __del__(self):
         try:
@@ -497,6 +516,21 @@ def _slos_methods():
         check(cdll().lwb_dist_create(self._h, n_modes, kmax, ptr(dense), C.byref(out)))
         return DeviceDistribution(self, out.value)
 
+    def dists_from_circuit(self, U_full, n_modes, in_states, threshold=1e-9, backend=BACKEND_PERMANENT, dtype=LWB_C128,  # noqa: N803
+                           comm=None):
+        """lwb_dists_from_circuit: full_probability_distribution of MANY input states of one circuit
+        (probability_distribution.py:127-133) into device-resident dense distributions of this context, one call and
+        one synchronisation; with a LOCAL communicator the inputs are computed round-robin on its GPUs."""
+        U_full = np.ascontiguousarray(U_full, dtype=np.complex128)  # noqa: N806
+        ins = np.ascontiguousarray(np.atleast_2d(in_states), dtype=np.uint8)
+        m_tot = U_full.shape[0]
+        if U_full.ndim != 2 or U_full.shape[1] != m_tot or ins.shape[1] != n_modes or n_modes > m_tot:
+            raise ValueError("unitary / state dimensions do not match")
+        slots = np.full(len(ins), -1, dtype=np.int32)
+        check(cdll().lwb_dists_from_circuit(self._h, comm.handle if comm is not None else None, ptr(U_full), m_tot, n_modes,
+                                            ptr(ins), len(ins), float(threshold), backend, dtype, ptr(slots)))
+        return [DeviceDistribution(self, int(sl)) for sl in slots]
+
     def dist_from_circuit(self, U_full, n_modes, in_state, threshold=1e-9, backend=BACKEND_PERMANENT, dtype=LWB_C128):  # noqa: N803
         """full_probability_distribution (permanent.py:116-163 / slos.py:43-80) into a device-resident dense
         distribution over K(n_modes, photons of in_state)."""
@@ -511,7 +545,7 @@ def _slos_methods():
         return DeviceDistribution(self, out.value)
 
     for f in (slos_amplitudes, slos_basis_probs, slos_basis_probs_dev, slos_amplitudes_dev, pdist, sample, sample_dev,
-              basis_sample, dist_zeros, dist_from_dense, dist_from_circuit):
+              basis_sample, dist_zeros, dist_from_dense, dist_from_circuit, dists_from_circuit):
         setattr(Context, f.__name__, f)
 
 
@@ -552,6 +586,144 @@ def _dev_methods():
 
 
 _dev_methods()
+
+
+# ---- multi-GPU communicators (include/lwb200.h "multi-GPU") ---------------------------------------------
+def shard_cuts(m: int, n: int, fractions) -> list[int]:
+    """lwb_shard_cuts: fock_basis ranks where the cumulative work of the permanent walk reaches the given fractions."""
+    fr = np.ascontiguousarray(fractions, dtype=np.float64)
+    cuts = np.zeros(len(fr), dtype=np.uint64)
+    check(cdll().lwb_shard_cuts(m, n, len(fr), ptr(fr), ptr(cuts)))
+    return [int(v) for v in cuts]
+
+
+class DevicePointer:
+    """A library-owned device buffer as a `__cuda_array_interface__` object (torch.as_tensor / cupy.asarray view it
+    without copying).  Valid until the communicator reallocates or is destroyed."""
+
+    def __init__(self, address: int, count: int, typestr: str = "<f8"):
+        self.address, self.count = address, count
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (address, False), "version": 3,
+                                         "strides": None}
+
+
+class Comm:
+    """lwb_comm: the hot path sharded over several GPUs.  `Comm.local(n)` - this process drives n GPUs;
+    `Comm.rank(ctx, rank, world, unique_id)` - one process per GPU, NCCL-bootstrapped (unique_id from
+    `Comm.unique_id()` on rank 0, broadcast by the host framework)."""
+
+    def __init__(self, handle, ctx=None):
+        self._c, self._ctx = handle, ctx
+        self._contexts: dict[int, Context] = {}
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(cdll().lwb_comm_unique_id(buf))
+        return buf.raw
+
+    @classmethod
+    def local(cls, n_gpus: int) -> "Comm":
+        h = C.c_void_p(0)
+        check(cdll().lwb_comm_init_local(int(n_gpus), C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def rank(cls, ctx: Context, rank: int, world: int, unique_id: bytes) -> "Comm":
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of Comm.unique_id()")
+        h = C.c_void_p(0)
+        check(cdll().lwb_comm_init_rank(ctx.handle, rank, world, C.create_string_buffer(unique_id, 128), C.byref(h)))
+        return cls(h, ctx)
+
+    @property
+    def handle(self):
+        return self._c
+
+    def close(self):
+        if self._c:
+            self._contexts.clear()
+            cdll().lwb_comm_destroy(self._c)
+            self._c = C.c_void_p(0)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        r, w, k, p = C.c_int(0), C.c_int(0), C.c_int(0), C.c_int(0)
+        check(cdll().lwb_comm_info(self._c, C.byref(r), C.byref(w), C.byref(k), C.byref(p)))
+        return {"rank": r.value, "world": w.value, "kind": "rank" if k.value else "local", "peer_stores": bool(p.value)}
+
+    def set_option(self, name: str, value: int):
+        check(cdll().lwb_comm_set_option(self._c, name.encode(), int(value)))
+
+    def context(self, index: int = 0) -> Context:
+        """The Context of device `index` (LOCAL) / the rank's own context (RANK, index 0); owned by the communicator."""
+        if index not in self._contexts:
+            h = C.c_void_p(0)
+            check(cdll().lwb_comm_handle(self._c, index, C.byref(h)))
+            self._contexts[index] = Context(index, _borrowed=h)
+        return self._contexts[index]
+
+    def shard(self, m: int, n: int, rank: int) -> tuple[int, int]:
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        check(cdll().lwb_comm_shard(self._c, m, n, rank, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def perm_basis_probs(self, U, in_state, dtype: int = LWB_C128, gather_host: bool = True, out=None, want_probs=True):  # noqa: N803
+        """Whole-basis probabilities sharded over the communicator -> (probs float64[S] | None, sum of probabilities)."""
+        U = np.ascontiguousarray(U, dtype=np.complex128)  # noqa: N806
+        s = _u8(in_state)
+        m = U.shape[0]
+        if U.ndim != 2 or U.shape[1] != m or len(s) != m:
+            raise ValueError("unitary / state dimensions do not match")
+        if want_probs and out is None:
+            out = np.zeros(fock_count(m, int(s.sum())), dtype=np.float64)
+        total = C.c_double(0)
+        check(cdll().lwb_comm_perm_basis_probs(self._c, ptr(U), m, ptr(s), dtype, int(gather_host),
+                                               ptr(out) if want_probs else None, C.byref(total)))
+        return (out if want_probs else None), float(total.value)
+
+    def perm_basis_probs_dev(self, d_U, m: int, d_in_state, n_photons: int, dtype: int = LWB_C128):  # noqa: N803
+        """RANK communicators, device inputs, asynchronous: (DevicePointer of this rank's complete distribution,
+        DevicePointer of the all-reduced sum)."""
+        p, q = C.c_void_p(0), C.c_void_p(0)
+        check(cdll().lwb_comm_perm_basis_probs_dev(self._c, ptr(d_U), m, ptr(d_in_state), n_photons, dtype, C.byref(p),
+                                                   C.byref(q)))
+        return DevicePointer(int(p.value), fock_count(m, n_photons)), DevicePointer(int(q.value), 1)
+
+    def pdist(self, U_full, n_modes, in_state, threshold=1e-9, dtype=LWB_C128):  # noqa: N803
+        """Context.pdist(backend = permanent) with the permanents sharded over the communicator."""
+        from math import comb
+
+        U_full = np.ascontiguousarray(U_full, dtype=np.complex128)  # noqa: N806
+        s = _u8(in_state)
+        m_tot = U_full.shape[0]
+        if U_full.ndim != 2 or U_full.shape[1] != m_tot or len(s) != n_modes or n_modes > m_tot:
+            raise ValueError("unitary / state dimensions do not match")
+        n = int(s.sum())
+        cap = comb(m_tot + n - 1, n) if m_tot == n_modes else sum(comb(n_modes + k - 1, k) for k in range(n + 1)) + 1
+        keys = np.zeros((cap, n_modes), dtype=np.uint8)
+        vals = np.zeros(cap, dtype=np.float64)
+        count = C.c_uint64(0)
+        check(cdll().lwb_comm_pdist(self._c, ptr(U_full), m_tot, n_modes, ptr(s), float(threshold), dtype, ptr(keys),
+                                    ptr(vals), cap, C.byref(count)))
+        k = int(count.value)
+        return keys[:k], vals[:k]
+
+    def perm_single(self, A, dtype: int = LWB_C128) -> complex:  # noqa: N803
+        A = np.ascontiguousarray(A, dtype=np.complex128)  # noqa: N806
+        if A.ndim != 2 or A.shape[0] != A.shape[1]:
+            raise ValueError("expected a square matrix")
+        out = np.zeros(2)
+        check(cdll().lwb_comm_perm_single(self._c, ptr(A), A.shape[0], dtype, ptr(out)))
+        return complex(out[0], out[1])
+
+    def perm_single_dev(self, d_A, n: int, d_out2, dtype: int = LWB_C128):  # noqa: N803
+        check(cdll().lwb_comm_perm_single_dev(self._c, ptr(d_A), n, dtype, ptr(d_out2)))
 
 
 def set_option(name: str, value: int):

@@ -27,6 +27,31 @@ _state_cls = State
 _settings = None
 _convolve_on_gpu = False
 _native_source = True
+_n_gpus = 1          # install(n_gpus=N) / set_n_gpus(N): GPUs one process spreads the hot path over
+_comm = None         # the LOCAL communicator shared by every backend object of this process
+
+
+def set_n_gpus(n_gpus: int) -> None:
+    """Spread the hot path of every B200 backend of this process over `n_gpus` GPUs: the output
+    states of PermanentBackend.full_probability_distribution (permanent.py:145-157) are sharded by equal-work rank
+    ranges, the unique sub-inputs of an imperfect source (probability_distribution.py:127-133) run round-robin.
+    1 restores the single-device path."""
+    global _n_gpus, _comm
+    n_gpus = int(n_gpus)
+    if n_gpus < 1:
+        raise ValueError("n_gpus must be >= 1")
+    if n_gpus != _n_gpus and _comm is not None:
+        _comm.close()
+        _comm = None
+    _n_gpus = n_gpus
+
+
+def local_comm():
+    """The process-wide LOCAL communicator (None on one GPU); created on first use, fails loudly without the devices."""
+    global _comm
+    if _n_gpus > 1 and _comm is None:
+        _comm = _lib.Comm.local(_n_gpus)
+    return _comm
 
 
 def set_native_source_statistics(flag: bool) -> None:
@@ -97,7 +122,9 @@ class _B200Base:
     @property
     def ctx(self) -> _lib.Context:
         if self._ctx is None:
-            self._ctx = _lib.default_context(self._device)
+            comm = local_comm() if self._device is None else None
+            # with a LOCAL communicator device 0's context is the communicator's own (one set of buffers per device)
+            self._ctx = comm.context(0) if comm is not None else _lib.default_context(self._device)
         return self._ctx
 
     def _pdist_arrays(self, circuit, input_state, backend_id):
@@ -105,6 +132,10 @@ class _B200Base:
         ins = _as_list(input_state)
         if len(ins) != circuit.n_modes:
             raise ValueError("input state length does not match the circuit")
+        comm = local_comm() if self._device is None else None
+        if comm is not None and backend_id == _lib.BACKEND_PERMANENT and sum(ins) >= 7:
+            # permanents sharded over the GPUs (SLOS layers depend on the whole previous layer: replicas only)
+            return comm.pdist(U, circuit.n_modes, ins, _threshold(), self._dtype)
         return self.ctx.pdist(U, circuit.n_modes, ins, _threshold(), backend_id, self._dtype)
 
 
@@ -251,14 +282,14 @@ class Backend:
 _installed = None
 
 
-def install(dtype: str = "complex128", device: int | None = None, patch_names: bool = True):
+def install(dtype: str = "complex128", device: int | None = None, patch_names: bool = True, n_gpus: int | None = None):
     """Make `lightworks.emulator.Backend("permanent" | "slos")` run on the GPU.
 
     Rebinds Backend._backend_map (a plain class attribute, backend.py:42-45) to subclasses of the
     reference's FockBackend built here; the reference CPU backends stay reachable as
     "permanent_cpu" / "slos_cpu".  With patch_names, `lightworks.emulator.backends.PermanentBackend`
     / `.SLOSBackend` (the names user code imports) are rebound too; the reference classes stay in
-    their defining modules.  Returns (B200PermanentBackend, B200SLOSBackend).
+    their defining modules.  n_gpus > 1: see set_n_gpus.  Returns (B200PermanentBackend, B200SLOSBackend).
     """
     global _installed, _state_cls, _settings
     import lightworks as lw
@@ -274,6 +305,8 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
     from lightworks.sdk.utils.exceptions import PhotonNumberError as LwPhotonNumberError
     from lightworks.sdk.utils.heralding import add_heralds_to_state
 
+    if n_gpus is not None:
+        set_n_gpus(n_gpus)
     if _installed is not None:
         return _installed["classes"]
     _state_cls = lw.State

@@ -83,6 +83,21 @@ class DistributionAlgebra:
         self.n_convolutions = 0
         self._vacuum = None
 
+    def prefetch(self, states) -> None:
+        """Every unique input of the source in ONE call (lwb_dists_from_circuit): no per-input synchronisation, and
+        with install(n_gpus=N) / set_n_gpus(N) the inputs are computed round-robin on the N GPUs."""
+        from .backends import local_comm
+
+        todo = [s for s in dict.fromkeys(states) if s not in self._unique]
+        if not todo:
+            return
+        comm = local_comm()
+        if comm is not None and comm.context(0) is not self.ctx:
+            comm = None  # the slots must live where the convolutions run
+        dists = self.ctx.dists_from_circuit(self.circuit.U_full, self.circuit.n_modes, [list(s) for s in todo],
+                                            self.threshold, self.backend_id, self.dtype, comm=comm)
+        self._unique.update(zip(todo, dists))
+
     def unique(self, state: tuple) -> _lib.DeviceDistribution:
         """probability_func(circuit, in_state) for one unique input (probability_distribution.py:124-129)."""
         d = self._unique.get(state)
@@ -145,6 +160,7 @@ def pdist_calc(circuit, inputs, backend, keep_on_device: bool = False):
                 s = tuple(istate.s if hasattr(istate, "s") else istate)
                 combos.append(([s[:n_modes] if len(s) > n_modes else s], float(prob)))
     kmax = max(sum(sum(s) for s in states) for states, _ in combos)
+    alg.prefetch(st for states, _ in combos for st in states)
     acc = ctx.dist_zeros(n_modes, kmax)
     # sum_inputs p * D_G (*) prod(rest) = sum_G D_G (*) ( sum_rest p * prod(rest) ) by linearity: the inputs are grouped
     # by their largest photon group G (for a Source: the mutually indistinguishable photons), the cheap products of

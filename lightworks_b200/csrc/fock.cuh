@@ -26,7 +26,16 @@
 #define LWB_MAX_MODES 128
 #define LWB_MAX_PHOTONS 40
 
+#define LWB_MAX_PEERS 15 /* extra destinations of a probability store: the other GPUs of one NVLink domain */
+
 namespace lwb {
+
+// Extra destinations of every probability a kernel stores: the same element of the peers' buffers (device
+// pointers into peer memory over NVLink, already offset like the local pointer).  n == 0: local store only.
+struct MirrorSet {
+    int n;
+    double* p[LWB_MAX_PEERS];
+};
 
 // Host-side table fill (exact until saturation).
 inline void fill_binomials(uint64_t* bin) {

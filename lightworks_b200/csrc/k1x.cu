@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/lwb200.h"
@@ -374,10 +375,10 @@ struct K1xTable<1> {
 
 int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, const double2* d_U, int m,
                     const uint8_t* d_in_state, int n, uint64_t r0, uint64_t cnt, double* d_probs, uint64_t* launches,
-                    std::string* err) {
+                    std::string* err, const MirrorSet* mirrors) {
     static K1xFn table[K1X_MAX_N + 1];
-    static bool table_init = false;
-    if (!table_init) {
+    static std::once_flag table_once;  // contexts of several GPUs may make their first call concurrently
+    std::call_once(table_once, [] {
         K1xTable<K1X_STATIC_MIN_N - 1>::fill(table);
         const K1xStaticEntry* (*groups[])(int*) = LWB_K1XS_GROUPS;
         for (auto g : groups) {
@@ -385,8 +386,7 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
             const K1xStaticEntry* e = g(&c);
             for (int i = 0; i < c; ++i) table[e[i].n] = e[i].fn;
         }
-        table_init = true;
-    }
+    });
     if (!k1x_supported(n) || !table[n] || cnt >= (1ull << 32)) { *err = "k1x: unsupported size"; return LWB_E_LIMIT; }
     if (cnt == 0) return 0;
     Plan* pl = nullptr;
@@ -431,6 +431,8 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
     ka.bin = d_bin; ka.U = d_U; ka.m = m; ka.in_state = d_in_state; ka.r0 = r0; ka.meta = pl->d_meta; ka.prog = pl->d_prog;
     ka.layout = pl->d_layout; ka.bstart = st->d_bstart; ka.offsets = st->d_offsets; ka.counts = st->d_counts;
     ka.n_types = pl->n_types; ka.bucket = st->d_bucket; ka.probs = d_probs;
+    ka.mir.n = 0;
+    if (mirrors) ka.mir = *mirrors;
     const size_t smem = (size_t)m * (n | 1) * 16 + (size_t)n * tb * 4;
     K1xFn fn = table[n];
     if (smem > 48 * 1024) K1X_CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

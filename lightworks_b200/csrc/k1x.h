@@ -18,6 +18,8 @@
 
 #include <string>
 
+#include "fock.cuh"
+
 namespace lwb {
 
 struct K1xState;  // cached plans + scratch buffers (owned by the context)
@@ -31,6 +33,6 @@ int k1x_plan_info(int n, int t, int* n_types, int* s_out, int* d_out, int* T_out
 // Returns 0, or a negative LWB_E_* code with *err set.
 int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, const double2* d_U, int m,
                     const uint8_t* d_in_state, int n, uint64_t r0, uint64_t cnt, double* d_probs, uint64_t* launches,
-                    std::string* err);
+                    std::string* err, const MirrorSet* mirrors = nullptr);
 
 }  // namespace lwb

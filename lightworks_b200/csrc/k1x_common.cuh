@@ -58,6 +58,7 @@ struct K1xArgs {
     int n_types;
     const uint32_t* bucket;
     double* probs;
+    MirrorSet mir;  // peers that receive every probability as it is produced (multi-GPU: no gather step afterwards)
 };
 
 // per-N tuning of the fused kernel: low Gray bits unrolled in the static walks, blocks per SM asked of ptxas
@@ -328,7 +329,9 @@ __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
     const double scale = sqrt(fin_s * fout);
     const double f = (double)tm.factor;
     const double re = (f * sr) / scale, im = (f * si) / scale;
-    a.probs[k_out] = re * re + im * im;
+    const double pr_out = re * re + im * im;
+    a.probs[k_out] = pr_out;
+    for (int g = 0; g < a.mir.n; ++g) a.mir.p[g][k_out] = pr_out;  // fire-and-forget stores into peer memory
 }
 
 // (launch bounds: an explicit minBlocks of 1 makes ptxas schedule the walk ~25 % slower than none on B200)

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../include/lwb200.h"
+#include "lwb_internal.h"
 #include "dist_kernels.cuh"
 #include "fock.cuh"
 #include "k1x.h"
@@ -24,7 +25,8 @@ using namespace lwb;
 
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(int code, const char* fmt, ...) {
+namespace lwb {
+int fail(int code, const char* fmt, ...) {
     char buf[512];
     va_list ap;
     va_start(ap, fmt);
@@ -33,54 +35,18 @@ static int fail(int code, const char* fmt, ...) {
     g_err = buf;
     return code;
 }
-namespace lwb {
 int set_error(int code, const char* msg) { return fail(code, "%s", msg); }  // for the host-only units (source_stats.cpp)
 int g_source_string_keys = 0;  // lwb_set_option("source_string_keys", 1): force the string-key path of lwb_source_statistics
 }  // namespace lwb
-#define CU(call)                                                                                 \
-    do {                                                                                         \
-        cudaError_t e_ = (call);                                                                 \
-        if (e_ != cudaSuccess) return fail(LWB_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    } while (0)
-#define CK(expr)                 \
-    do {                         \
-        int rc_ = (expr);        \
-        if (rc_ != 0) return rc_; \
-    } while (0)
-
-struct Buf {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-struct lwb_context {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernel
-    cudaEvent_t chunk_done[8] = {};
-    uint64_t* d_bin = nullptr;
-    Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall, bCdf, bTile, bUni, bIdx;
-    uint64_t launches = 0;
-    K1xState* k1x = nullptr;
-    struct DistSlot {  // dense distribution over the key space K(n_modes, kmax), device resident
-        double* p = nullptr;
-        int n_modes = 0, kmin = 0, kmax = 0;
-        uint64_t size = 0;
-    };
-    std::vector<DistSlot> dists;
-    std::mutex mu;
-};
 
 static uint64_t g_bin[LWB_BIN_A * LWB_BIN_B];
 static std::once_flag g_bin_once;
-static const uint64_t* host_bin() {
+const uint64_t* lwb::host_bin() {
     std::call_once(g_bin_once, [] { fill_binomials(g_bin); });
     return g_bin;
 }
 
-static int ensure(lwb_handle h, Buf& b, size_t bytes) {
+int lwb::ensure(lwb_handle h, Buf& b, size_t bytes) {
     if (bytes <= b.cap) return 0;
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr;
@@ -132,6 +98,17 @@ static const K1Variant* pick_k1(int n) {
 }
 
 // ---- launch helpers ----------------------------------------------------------------------------
+int lwb::sum_doubles_dev(lwb_handle h, const double* d_x, uint64_t count, double* d_out) {
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((count + 4095) / 4096, (uint64_t)h->sm_count * 4));
+    CK(ensure(h, h->bPart, (size_t)std::max(grid, 1024u) * 16));
+    double* partials = (double*)h->bPart.p;
+    sum_slices_kernel<<<grid, SUM_THREADS, 0, h->stream>>>(d_x, count, partials);
+    sum_slices_kernel<<<1, SUM_THREADS, 0, h->stream>>>(partials, grid, d_out);
+    h->launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
 template <typename F>
 static int resident_blocks(lwb_handle h, F fn, size_t smem, int* out) {
     if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -247,13 +224,15 @@ int lwb_launch_count(lwb_handle h, uint64_t* count) {
 }
 
 // ---- Fock indexing (host) ----------------------------------------------------------------------
-static int check_mn(int m, int n) {
+}  // extern "C"
+int lwb::check_mn(int m, int n) {
     if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
     if (n < 0 || n > LWB_MAX_PHOTONS) return fail(LWB_E_LIMIT, "photons n=%d outside [0,%d]", n, LWB_MAX_PHOTONS);
     if (m + n - 1 >= LWB_BIN_A) return fail(LWB_E_LIMIT, "m+n too large");
     if (binom(host_bin(), m + n - 1, n) == UINT64_MAX) return fail(LWB_E_LIMIT, "Fock space exceeds 2^64");
     return 0;
 }
+extern "C" {
 
 int lwb_fock_count(int m, int n, uint64_t* count) {
     CK(check_mn(m, n));
@@ -383,9 +362,10 @@ int lwb_perm_matrices(lwb_handle h, const double* A, uint64_t B, int n, int dtyp
     return 0;
 }
 
-static int launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
-                         const uint8_t* d_outs, uint64_t r0, uint64_t n_out, int n, int dtype,
-                         int want_probs, double* d_out) {
+}  // extern "C"
+int lwb::launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
+                       const uint8_t* d_outs, uint64_t r0, uint64_t n_out, int n, int dtype,
+                       int want_probs, double* d_out) {
     if (dtype != LWB_C128 && dtype != LWB_C64) return fail(LWB_E_ARG, "dtype %d", dtype);
     if (n < 1 || n > LWB_K1_MAX_N) return fail(LWB_E_LIMIT, "batched permanents support 1 <= n <= %d photons (got %d)", LWB_K1_MAX_N, n);
     if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
@@ -396,7 +376,7 @@ static int launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* 
         // full-basis rank range: bunched output states repeat rows, walk prod(s_i+1)/2 terms instead of 2^(n-1)
         std::string err;
         int rc = k1x_basis_probs(h->k1x, h->stream, h->d_bin, (const double2*)d_U, m, d_ins, n, r0, n_out, d_out,
-                                 &h->launches, &err);
+                                 &h->launches, &err, &h->mirror);
         if (rc) return fail(rc, "%s", err.c_str());
         return 0;
     }
@@ -409,13 +389,15 @@ static int launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* 
     uint64_t need = (n_out + gpb - 1) / gpb;
     uint64_t gx = std::max<uint64_t>(1, (uint64_t)resident / (uint64_t)n_in);
     gx = std::min<uint64_t>(need, gx);
-    PermStatesArgs a{(const double2*)d_U, m, d_ins, d_outs, r0, n_out, h->d_bin, d_out, want_probs};
+    PermStatesArgs a{(const double2*)d_U, m, d_ins, d_outs, r0, n_out, h->d_bin, d_out, want_probs, h->mirror};
+    if (!want_probs) a.mir.n = 0;
     dim3 grid((unsigned)gx, (unsigned)n_in, 1);
     fn<<<grid, K1_THREADS, smem, h->stream>>>(a);
     h->launches++;
     CU(cudaGetLastError());
     return 0;
 }
+extern "C" {
 
 int lwb_perm_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
                             const uint8_t* d_outs, uint64_t n_out, int n_photons, int dtype,
@@ -671,7 +653,7 @@ static std::once_flag g_slos_once;
 static int launch_slos_layer(lwb_handle h, const SlosLayerArgs& a) {
     std::call_once(g_slos_once, [] { SlosTable<LWB_MAX_PHOTONS>::fill(g_slos); });
     const int k = a.k, m = a.m;
-    const int wide = a.S >= (1ull << 32) ? 1 : 0;
+    const int wide = a.S + 32ull * SLOS_ITERS >= (1ull << 32) ? 1 : 0;  // a lane overshoots S by up to 32 * SLOS_ITERS
     const size_t isz = wide ? 8 : 4;
     const size_t smem = (size_t)m * 16 + (size_t)((k + 2) & ~1) * 8 + 3 * (size_t)k * (m + 1) * isz;
     const uint64_t warps = (a.S + 32ull * SLOS_ITERS - 1) / (32ull * SLOS_ITERS);
@@ -773,6 +755,93 @@ static int slos_run_host(lwb_handle h, const double* U, int m, const uint8_t* in
     return 0;
 }
 
+// Steps 2a / 2b of full_probability_distribution from per-full-state probabilities already on the device
+// (fock_basis order for the permanent backend, and for SLOS with loss modes; SLOS order for lossless SLOS).
+int lwb::pdist_finish(lwb_handle h, const double* d_probs, int m_tot, int n_modes, int n, double threshold, int backend,
+                      uint8_t* keys, double* vals, uint64_t cap, uint64_t* count_out) {
+    const uint64_t* hb = host_bin();
+    const int loss = m_tot - n_modes;
+    const int order = backend == LWB_BACKEND_SLOS ? 1 : 0;
+    const uint64_t S = binom(hb, m_tot + n - 1, n);
+    if (loss == 0) {
+        // 2a. no loss modes: every full state is its own key; filter p > threshold in enumeration order
+        std::vector<double> p(S);
+        CU(cudaMemcpyAsync(p.data(), d_probs, S * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        int x[LWB_MAX_PHOTONS + 1];
+        for (int i = 0; i < n; ++i) x[i] = 0;  // first state in both orders: all photons in mode 0
+        uint64_t cnt = 0;
+        for (uint64_t r = 0; r < S; ++r) {
+            if (p[r] > threshold) {
+                if (cnt < cap) {
+                    modes_to_state(x, n, n_modes, keys + cnt * (uint64_t)n_modes);
+                    vals[cnt] = p[r];
+                }
+                ++cnt;
+            }
+            if (order == 0) colex_next(x, n, m_tot);
+            else lex_next(x, n, m_tot);
+        }
+        *count_out = cnt;
+        if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
+                                   (unsigned long long)cap);
+        return 0;
+    }
+
+    // 2b. loss modes: marginalise on the device, order the keys by first appearance on the host
+    const int k_min = backend == LWB_BACKEND_PERMANENT ? 1 : 0;  // permanent.py:148-149 skips zero-real-photon states
+    uint64_t key_off[LWB_MAX_PHOTONS + 3];
+    uint64_t nk = 0;
+    for (int kk = 0; kk <= n + 1; ++kk) {
+        key_off[kk] = nk;
+        if (kk >= k_min && kk <= n) nk += binom(hb, n_modes + kk - 1, kk);
+    }
+    CK(ensure(h, h->bMarg, nk * 8));
+    CK(ensure(h, h->bFirst, nk * 8));
+    CK(ensure(h, h->bSmall, 4096));
+    CU(cudaMemcpyAsync((char*)h->bSmall.p + 2048, key_off, sizeof(uint64_t) * (size_t)(n + 2), cudaMemcpyHostToDevice, h->stream));
+    MargArgs ma;
+    ma.bin = h->d_bin; ma.m_tot = m_tot; ma.n_modes = n_modes; ma.n = n; ma.k_min = k_min;
+    ma.key_off = (const uint64_t*)((char*)h->bSmall.p + 2048); ma.n_keys = nk; ma.probs = d_probs;
+    ma.threshold = threshold; ma.order = order; ma.marg = (double*)h->bMarg.p; ma.first_pos = (uint64_t*)h->bFirst.p;
+    CK(launch_kmax(h, n, nk, 0, ma, marginalise_kernel<4>, marginalise_kernel<8>, marginalise_kernel<12>,
+                   marginalise_kernel<16>, marginalise_kernel<24>, marginalise_kernel<40>));
+    std::vector<double> marg(nk);
+    std::vector<uint64_t> first(nk);
+    CU(cudaMemcpyAsync(marg.data(), h->bMarg.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(first.data(), h->bFirst.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    std::vector<uint64_t> idx;
+    for (uint64_t k = 0; k < nk; ++k)
+        if (first[k] != UINT64_MAX) idx.push_back(k);
+    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return first[a] < first[b]; });
+    uint64_t cnt = 0;
+    double total = 0.0;  // sum(pdist.values()) in dict order, permanent.py:159
+    for (uint64_t k : idx) {
+        int kk = k_min;
+        while (kk < n && k >= key_off[kk + 1]) ++kk;
+        if (cnt < cap) {
+            int x[LWB_MAX_PHOTONS + 1];
+            colex_unrank(hb, k - key_off[kk], kk, n_modes, x);
+            modes_to_state(x, kk, n_modes, keys + cnt * (uint64_t)n_modes);
+            vals[cnt] = marg[k];
+        }
+        total += marg[k];
+        ++cnt;
+    }
+    if (backend == LWB_BACKEND_PERMANENT && total < 1.0) {  // permanent.py:160-161 (loss_modes > 0 here)
+        if (cnt < cap) {
+            memset(keys + cnt * (uint64_t)n_modes, 0, (size_t)n_modes);
+            vals[cnt] = 1.0 - total;
+        }
+        ++cnt;
+    }
+    *count_out = cnt;
+    if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
+                               (unsigned long long)cap);
+    return 0;
+}
+
 extern "C" {
 
 int lwb_slos_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* in_state, int order, double* d_amps) {
@@ -823,7 +892,6 @@ int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const 
     CK(ensure(h, h->bU, (size_t)m_tot * m_tot * 16));
     CK(ensure(h, h->bProbs, S * 8));
     CU(cudaMemcpyAsync(h->bU.p, U_full, (size_t)m_tot * m_tot * 16, cudaMemcpyHostToDevice, h->stream));
-    const int order = backend == LWB_BACKEND_SLOS ? 1 : 0;
     if (backend == LWB_BACKEND_PERMANENT) {
         CK(ensure(h, h->bIn, (size_t)m_tot));
         CU(cudaMemcpyAsync(h->bIn.p, full_in, (size_t)m_tot, cudaMemcpyHostToDevice, h->stream));
@@ -834,83 +902,7 @@ int lwb_pdist(lwb_handle h, const double* U_full, int m_tot, int n_modes, const 
         CK(slos_run_dev(h, (const double*)h->bU.p, m_tot, full_in, loss == 0 ? 1 : 0, 1, (double*)h->bProbs.p));
     }
 
-    if (loss == 0) {
-        // 2a. no loss modes: every full state is its own key; filter p > threshold in enumeration order
-        std::vector<double> p(S);
-        CU(cudaMemcpyAsync(p.data(), h->bProbs.p, S * 8, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        int x[LWB_MAX_PHOTONS + 1];
-        for (int i = 0; i < n; ++i) x[i] = 0;  // first state in both orders: all photons in mode 0
-        uint64_t cnt = 0;
-        for (uint64_t r = 0; r < S; ++r) {
-            if (p[r] > threshold) {
-                if (cnt < cap) {
-                    modes_to_state(x, n, n_modes, keys + cnt * (uint64_t)n_modes);
-                    vals[cnt] = p[r];
-                }
-                ++cnt;
-            }
-            if (order == 0) colex_next(x, n, m_tot);
-            else lex_next(x, n, m_tot);
-        }
-        *count_out = cnt;
-        if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
-                                   (unsigned long long)cap);
-        return 0;
-    }
-
-    // 2b. loss modes: marginalise on the device, order the keys by first appearance on the host
-    const int k_min = backend == LWB_BACKEND_PERMANENT ? 1 : 0;  // permanent.py:148-149 skips zero-real-photon states
-    uint64_t key_off[LWB_MAX_PHOTONS + 3];
-    uint64_t nk = 0;
-    for (int kk = 0; kk <= n + 1; ++kk) {
-        key_off[kk] = nk;
-        if (kk >= k_min && kk <= n) nk += binom(hb, n_modes + kk - 1, kk);
-    }
-    CK(ensure(h, h->bMarg, nk * 8));
-    CK(ensure(h, h->bFirst, nk * 8));
-    CK(ensure(h, h->bSmall, 4096));
-    CU(cudaMemcpyAsync((char*)h->bSmall.p + 2048, key_off, sizeof(uint64_t) * (size_t)(n + 2), cudaMemcpyHostToDevice, h->stream));
-    MargArgs ma;
-    ma.bin = h->d_bin; ma.m_tot = m_tot; ma.n_modes = n_modes; ma.n = n; ma.k_min = k_min;
-    ma.key_off = (const uint64_t*)((char*)h->bSmall.p + 2048); ma.n_keys = nk; ma.probs = (const double*)h->bProbs.p;
-    ma.threshold = threshold; ma.order = order; ma.marg = (double*)h->bMarg.p; ma.first_pos = (uint64_t*)h->bFirst.p;
-    CK(launch_kmax(h, n, nk, 0, ma, marginalise_kernel<4>, marginalise_kernel<8>, marginalise_kernel<12>,
-                   marginalise_kernel<16>, marginalise_kernel<24>, marginalise_kernel<40>));
-    std::vector<double> marg(nk);
-    std::vector<uint64_t> first(nk);
-    CU(cudaMemcpyAsync(marg.data(), h->bMarg.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaMemcpyAsync(first.data(), h->bFirst.p, nk * 8, cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    std::vector<uint64_t> idx;
-    for (uint64_t k = 0; k < nk; ++k)
-        if (first[k] != UINT64_MAX) idx.push_back(k);
-    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return first[a] < first[b]; });
-    uint64_t cnt = 0;
-    double total = 0.0;  // sum(pdist.values()) in dict order, permanent.py:159
-    for (uint64_t k : idx) {
-        int kk = k_min;
-        while (kk < n && k >= key_off[kk + 1]) ++kk;
-        if (cnt < cap) {
-            int x[LWB_MAX_PHOTONS + 1];
-            colex_unrank(hb, k - key_off[kk], kk, n_modes, x);
-            modes_to_state(x, kk, n_modes, keys + cnt * (uint64_t)n_modes);
-            vals[cnt] = marg[k];
-        }
-        total += marg[k];
-        ++cnt;
-    }
-    if (backend == LWB_BACKEND_PERMANENT && total < 1.0) {  // permanent.py:160-161 (loss_modes > 0 here)
-        if (cnt < cap) {
-            memset(keys + cnt * (uint64_t)n_modes, 0, (size_t)n_modes);
-            vals[cnt] = 1.0 - total;
-        }
-        ++cnt;
-    }
-    *count_out = cnt;
-    if (cnt > cap) return fail(LWB_E_LIMIT, "distribution has %llu entries, capacity %llu", (unsigned long long)cnt,
-                               (unsigned long long)cap);
-    return 0;
+    return pdist_finish(h, (const double*)h->bProbs.p, m_tot, n_modes, n, threshold, backend, keys, vals, cap, count_out);
 }
 
 }  // extern "C"
@@ -1047,6 +1039,76 @@ static int get_slot(lwb_handle h, int slot, lwb_context::DistSlot** d) {
     return 0;
 }
 
+int lwb::new_dist_slot(lwb_handle h, int n_modes, int kmin, int kmax, int* slot) { return new_slot(h, n_modes, kmin, kmax, slot); }
+
+// full_probability_distribution (permanent.py:116-163 / slos.py:43-80) into the dense key-space vector d_dst
+// (K(n_modes, n) entries, on h's device), everything enqueued on h->stream, no synchronisation.
+int lwb::dist_from_circuit_enqueue(lwb_handle h, const double* d_U_full, int m_tot, int n_modes, const uint8_t* in_state,
+                                   double threshold, int backend, int dtype, double* d_dst, uint64_t dst_size) {
+    const uint64_t* hb = host_bin();
+    const int loss = m_tot - n_modes;
+    int n = 0;
+    for (int i = 0; i < n_modes; ++i) n += in_state[i];
+    CK(check_mn(m_tot, n));
+    if (backend == LWB_BACKEND_PERMANENT && n > LWB_K1_MAX_N)
+        return fail(LWB_E_LIMIT, "permanent backend supports up to %d photons (got %d)", LWB_K1_MAX_N, n);
+    CU(cudaMemsetAsync(d_dst, 0, dst_size * 8, h->stream));
+    if (n == 0) {  // permanent.py:137-138, slos.py:64-65
+        const double one = 1.0;
+        CU(cudaMemcpyAsync(d_dst, &one, 8, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    uint8_t full_in[LWB_MAX_MODES];
+    memset(full_in, 0, sizeof full_in);
+    memcpy(full_in, in_state, (size_t)n_modes);  // permanent.py:142-143, slos.py:69-70
+    const uint64_t S = binom(hb, m_tot + n - 1, n);
+    CK(ensure(h, h->bProbs, S * 8));
+    if (backend == LWB_BACKEND_PERMANENT) {
+        CK(ensure(h, h->bIn, (size_t)LWB_MAX_MODES));
+        CU(cudaMemcpyAsync(h->bIn.p, full_in, (size_t)m_tot, cudaMemcpyHostToDevice, h->stream));  // pageable: staged before return
+        CK(launch_states(h, d_U_full, m_tot, (const uint8_t*)h->bIn.p, 1, nullptr, 0, S, n, dtype, 1, (double*)h->bProbs.p));
+    } else {
+        CK(slos_run_dev(h, d_U_full, m_tot, full_in, 0, 1, (double*)h->bProbs.p));  // fock_basis order
+    }
+    if (loss == 0) {
+        dist_threshold_copy_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(d_dst + keyspace_off(n_modes, n),
+                                                                                       (const double*)h->bProbs.p, threshold, S);
+        h->launches++;
+        CU(cudaGetLastError());
+        return 0;
+    }
+    // loss modes: marginalise straight into the key space (the marginal table IS the key-space layout)
+    const int k_min = backend == LWB_BACKEND_PERMANENT ? 1 : 0;  // permanent.py:148-149 skips zero-real-photon states
+    uint64_t key_off[LWB_MAX_PHOTONS + 3];
+    uint64_t nk = 0;
+    for (int kk = 0; kk <= n + 1; ++kk) {
+        key_off[kk] = nk;
+        if (kk >= k_min && kk <= n) nk += binom(hb, n_modes + kk - 1, kk);
+    }
+    CK(ensure(h, h->bFirst, nk * 8));
+    CK(ensure(h, h->bSmall, 4096));
+    CU(cudaMemcpyAsync((char*)h->bSmall.p + 2048, key_off, sizeof(uint64_t) * (size_t)(n + 2), cudaMemcpyHostToDevice, h->stream));
+    double* marg = d_dst + (k_min ? 1 : 0);
+    MargArgs ma;
+    ma.bin = h->d_bin; ma.m_tot = m_tot; ma.n_modes = n_modes; ma.n = n; ma.k_min = k_min;
+    ma.key_off = (const uint64_t*)((char*)h->bSmall.p + 2048); ma.n_keys = nk; ma.probs = (const double*)h->bProbs.p;
+    ma.threshold = threshold; ma.order = 0; ma.marg = marg; ma.first_pos = (uint64_t*)h->bFirst.p;
+    CK(launch_kmax(h, n, nk, 0, ma, marginalise_kernel<4>, marginalise_kernel<8>, marginalise_kernel<12>,
+                   marginalise_kernel<16>, marginalise_kernel<24>, marginalise_kernel<40>));
+    if (backend == LWB_BACKEND_PERMANENT) {  // permanent.py:159-161: vacuum = 1 - sum if sum < 1
+        const uint64_t n_tiles = (nk + SCAN_TILE - 1) / SCAN_TILE;
+        CK(ensure(h, h->bTile, (2 * n_tiles + 1) * 8));
+        double* tile_sum = (double*)h->bTile.p;
+        double* tile_off = tile_sum + n_tiles;
+        scan_tile_sums_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(marg, nk, -1.0, tile_sum);
+        scan_tile_offsets_kernel<<<1, 1024, 0, h->stream>>>(tile_sum, n_tiles, tile_off);
+        dist_vacuum_kernel<<<1, 32, 0, h->stream>>>(d_dst, tile_off + n_tiles);
+        h->launches += 3;
+        CU(cudaGetLastError());
+    }
+    return 0;
+}
+
 extern "C" {
 
 int lwb_keyspace_size(int n_modes, int kmax, uint64_t* size) {
@@ -1108,9 +1170,10 @@ int lwb_dist_create(lwb_handle h, int n_modes, int kmax, const double* dense, in
 }
 
 int lwb_dist_free(lwb_handle h, int slot) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
     lwb_context::DistSlot* d = nullptr;
     CK(get_slot(h, slot, &d));
-    std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaFree(d->p));
@@ -1140,13 +1203,14 @@ int lwb_dist_download(lwb_handle h, int slot, double* dense) {
 }
 
 int lwb_dist_axpy(lwb_handle h, int slot_acc, double alpha, int slot_x) {
+    if (!h) return fail(LWB_E_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
     lwb_context::DistSlot *acc = nullptr, *x = nullptr;
     CK(get_slot(h, slot_acc, &acc));
     CK(get_slot(h, slot_x, &x));
     if (acc->n_modes != x->n_modes || acc->kmax < x->kmax)
         return fail(LWB_E_ARG, "accumulator (%d modes, <= %d photons) cannot hold (%d modes, <= %d photons)", acc->n_modes,
                     acc->kmax, x->n_modes, x->kmax);
-    std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     dist_axpy_kernel<<<(unsigned)((x->size + 255) / 256), 256, 0, h->stream>>>(acc->p, alpha, x->p, x->size);
     h->launches++;
@@ -1156,12 +1220,12 @@ int lwb_dist_axpy(lwb_handle h, int slot_acc, double alpha, int slot_x) {
 }
 
 int lwb_dist_convolve(lwb_handle h, int slot_a, int slot_b, int* slot_out) {
+    if (!h || !slot_out) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
     lwb_context::DistSlot *pa = nullptr, *pb = nullptr;
     CK(get_slot(h, slot_a, &pa));
     CK(get_slot(h, slot_b, &pb));
-    if (!slot_out) return fail(LWB_E_ARG, "null argument");
     if (pa->n_modes != pb->n_modes) return fail(LWB_E_ARG, "mode counts differ (%d, %d)", pa->n_modes, pb->n_modes);
-    std::lock_guard<std::mutex> lk(h->mu);
     CU(cudaSetDevice(h->device));
     const lwb_context::DistSlot A = *pa, B = *pb;  // new_slot may move the vector
     CK(new_slot(h, A.n_modes, A.kmin + B.kmin, A.kmax + B.kmax, slot_out));
@@ -1170,9 +1234,14 @@ int lwb_dist_convolve(lwb_handle h, int slot_a, int slot_b, int* slot_out) {
     ca.bin = h->d_bin; ca.n_modes = A.n_modes; ca.ka_min = A.kmin; ca.ka_max = A.kmax; ca.kb_min = B.kmin; ca.kb_max = B.kmax;
     ca.A = A.p; ca.B = B.p; ca.out = o.p; ca.size_out = o.size;
     for (int k = 0; k <= o.kmax + 1; ++k) ca.off[k] = keyspace_off(A.n_modes, k);
-    CK(launch_kmax(h, o.kmax, o.size, 0, ca, convolve_kernel<4>, convolve_kernel<8>, convolve_kernel<12>, convolve_kernel<16>,
-                   convolve_kernel<24>, convolve_kernel<40>));
-    return 0;
+    const int rc = launch_kmax(h, o.kmax, o.size, 0, ca, convolve_kernel<4>, convolve_kernel<8>, convolve_kernel<12>,
+                               convolve_kernel<16>, convolve_kernel<24>, convolve_kernel<40>);
+    if (rc) {  // leave no slot behind on failure
+        cudaFree(h->dists[*slot_out].p);
+        h->dists[*slot_out] = lwb_context::DistSlot();
+        *slot_out = -1;
+    }
+    return rc;
 }
 
 int lwb_dist_sample(lwb_handle h, int slot, const double* uniform, uint64_t n_samples, uint64_t* index, double* total) {
@@ -1186,82 +1255,7 @@ int lwb_dist_sample(lwb_handle h, int slot, const double* uniform, uint64_t n_sa
 
 int lwb_dist_from_circuit(lwb_handle h, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state,
                           double threshold, int backend, int dtype, int* slot) {
-    if (!h || !U_full || !in_state || !slot) return fail(LWB_E_ARG, "null argument");
-    if (backend != LWB_BACKEND_PERMANENT && backend != LWB_BACKEND_SLOS) return fail(LWB_E_ARG, "backend %d", backend);
-    if (n_modes < 1 || n_modes > m_tot) return fail(LWB_E_ARG, "n_modes=%d outside [1,%d]", n_modes, m_tot);
-    if (m_tot > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m_tot, LWB_MAX_MODES);
-    std::lock_guard<std::mutex> lk(h->mu);
-    const uint64_t* hb = host_bin();
-    const int loss = m_tot - n_modes;
-    int n = 0;
-    for (int i = 0; i < n_modes; ++i) n += in_state[i];
-    CK(check_mn(m_tot, n));
-    if (backend == LWB_BACKEND_PERMANENT && n > LWB_K1_MAX_N)
-        return fail(LWB_E_LIMIT, "permanent backend supports up to %d photons (got %d)", LWB_K1_MAX_N, n);
-    CU(cudaSetDevice(h->device));
-    CK(new_slot(h, n_modes, loss ? 0 : n, n, slot));
-    const auto d = h->dists[*slot];
-    CU(cudaMemsetAsync(d.p, 0, d.size * 8, h->stream));
-    if (n == 0) {  // permanent.py:137-138, slos.py:64-65
-        const double one = 1.0;
-        CU(cudaMemcpyAsync(d.p, &one, 8, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        return 0;
-    }
-    uint8_t full_in[LWB_MAX_MODES];
-    memset(full_in, 0, sizeof full_in);
-    memcpy(full_in, in_state, (size_t)n_modes);  // permanent.py:142-143, slos.py:69-70
-    const uint64_t S = binom(hb, m_tot + n - 1, n);
-    CK(ensure(h, h->bU, (size_t)m_tot * m_tot * 16));
-    CK(ensure(h, h->bProbs, S * 8));
-    CU(cudaMemcpyAsync(h->bU.p, U_full, (size_t)m_tot * m_tot * 16, cudaMemcpyHostToDevice, h->stream));
-    if (backend == LWB_BACKEND_PERMANENT) {
-        CK(ensure(h, h->bIn, (size_t)m_tot));
-        CU(cudaMemcpyAsync(h->bIn.p, full_in, (size_t)m_tot, cudaMemcpyHostToDevice, h->stream));
-        CK(launch_states(h, (const double*)h->bU.p, m_tot, (const uint8_t*)h->bIn.p, 1, nullptr, 0, S, n, dtype, 1,
-                         (double*)h->bProbs.p));
-    } else {
-        CK(slos_run_dev(h, (const double*)h->bU.p, m_tot, full_in, 0, 1, (double*)h->bProbs.p));  // fock_basis order
-    }
-    if (loss == 0) {
-        dist_threshold_copy_kernel<<<(unsigned)((S + 255) / 256), 256, 0, h->stream>>>(d.p + keyspace_off(n_modes, n),
-                                                                                       (const double*)h->bProbs.p, threshold, S);
-        h->launches++;
-        CU(cudaGetLastError());
-        CU(cudaStreamSynchronize(h->stream));  // full_in / U_full are the caller's
-        return 0;
-    }
-    // loss modes: marginalise straight into the key space (the marginal table IS the key-space layout)
-    const int k_min = backend == LWB_BACKEND_PERMANENT ? 1 : 0;  // permanent.py:148-149 skips zero-real-photon states
-    uint64_t key_off[LWB_MAX_PHOTONS + 3];
-    uint64_t nk = 0;
-    for (int kk = 0; kk <= n + 1; ++kk) {
-        key_off[kk] = nk;
-        if (kk >= k_min && kk <= n) nk += binom(hb, n_modes + kk - 1, kk);
-    }
-    CK(ensure(h, h->bFirst, nk * 8));
-    CK(ensure(h, h->bSmall, 4096));
-    CU(cudaMemcpyAsync((char*)h->bSmall.p + 2048, key_off, sizeof(uint64_t) * (size_t)(n + 2), cudaMemcpyHostToDevice, h->stream));
-    double* marg = d.p + (k_min ? 1 : 0);
-    MargArgs ma;
-    ma.bin = h->d_bin; ma.m_tot = m_tot; ma.n_modes = n_modes; ma.n = n; ma.k_min = k_min;
-    ma.key_off = (const uint64_t*)((char*)h->bSmall.p + 2048); ma.n_keys = nk; ma.probs = (const double*)h->bProbs.p;
-    ma.threshold = threshold; ma.order = 0; ma.marg = marg; ma.first_pos = (uint64_t*)h->bFirst.p;
-    CK(launch_kmax(h, n, nk, 0, ma, marginalise_kernel<4>, marginalise_kernel<8>, marginalise_kernel<12>,
-                   marginalise_kernel<16>, marginalise_kernel<24>, marginalise_kernel<40>));
-    if (backend == LWB_BACKEND_PERMANENT) {  // permanent.py:159-161: vacuum = 1 - sum if sum < 1
-        const uint64_t n_tiles = (nk + SCAN_TILE - 1) / SCAN_TILE;
-        CK(ensure(h, h->bTile, (2 * n_tiles + 1) * 8));
-        double* tile_sum = (double*)h->bTile.p;
-        double* tile_off = tile_sum + n_tiles;
-        scan_tile_sums_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, h->stream>>>(marg, nk, -1.0, tile_sum);
-        scan_tile_offsets_kernel<<<1, 1024, 0, h->stream>>>(tile_sum, n_tiles, tile_off);
-        dist_vacuum_kernel<<<1, 32, 0, h->stream>>>(d.p, tile_off + n_tiles);
-        h->launches += 3;
-        CU(cudaGetLastError());
-    }
-    CU(cudaStreamSynchronize(h->stream));
-    return 0;
+    return lwb_dists_from_circuit(h, nullptr, U_full, m_tot, n_modes, in_state, 1, threshold, backend, dtype, slot);
 }
 
 }  // extern "C"

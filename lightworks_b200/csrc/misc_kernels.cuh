@@ -25,6 +25,25 @@ static __global__ void fock_basis_kernel(const uint64_t* __restrict__ bin, int m
     }
 }
 
+// Deterministic sum of `count` doubles: block b adds the contiguous slice [b, b+1) * ceil(count / grid) with a fixed
+// thread-strided order and a fixed shared-memory tree; a second launch (grid 1) adds the block partials the same way.
+constexpr int SUM_THREADS = 256;
+static __global__ void __launch_bounds__(SUM_THREADS) sum_slices_kernel(const double* __restrict__ x, uint64_t count,
+                                                                       double* __restrict__ partials) {
+    __shared__ double sh[SUM_THREADS];
+    const uint64_t per = (count + gridDim.x - 1) / gridDim.x;
+    const uint64_t b = per * blockIdx.x, e = (b + per < count) ? b + per : count;
+    double acc = 0.0;
+    for (uint64_t i = b + threadIdx.x; i < e; i += SUM_THREADS) acc += x[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = SUM_THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = sh[0];
+}
+
 // FP64 roofline denominator: 8 independent DFMA chains per thread, no memory traffic.
 constexpr int DFMA_PER_ITER = 8;
 static __global__ void dfma_peak_kernel(double* out, int iters, double a) {

@@ -70,6 +70,7 @@ struct PermStatesArgs {
     const uint64_t* bin;       // binomial table (device)
     double* out;               // [n_in][n_out] complex (2 doubles) or real
     int out_probs;             // 0: amplitudes, 1: |amp|^2
+    MirrorSet mir;             // out_probs only: peers that receive every probability as it is produced
 };
 
 template <typename T>
@@ -169,8 +170,11 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
             const double scale = sqrt(fin * fout);
             const double re = (2.0 * dr) / scale, im = (2.0 * di) / scale;
             const uint64_t o = it_begin + it;
-            if (a.out_probs) outp[o] = re * re + im * im;
-            else { outp[2 * o] = re; outp[2 * o + 1] = im; }
+            if (a.out_probs) {
+                const double pr_out = re * re + im * im;
+                outp[o] = pr_out;
+                for (int g = 0; g < a.mir.n; ++g) a.mir.p[g][(size_t)blockIdx.y * a.n_out + o] = pr_out;
+            } else { outp[2 * o] = re; outp[2 * o + 1] = im; }
             // advance to the next output state
             if (it + 1 < my_len) {
                 if (a.out_states) {

@@ -2,8 +2,10 @@
 #pragma once
 #include "perm_kernels.cuh"
 
+#ifndef LWB_K1_MAX_N
 #define LWB_K1_MAX_N 24
 #define LWB_K2_MAX_N 40
+#endif
 
 namespace lwb {
 

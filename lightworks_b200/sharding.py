@@ -115,11 +115,13 @@ STATE_OVERHEAD_TERMS = 63.0
 def work_cuts(m: int, n: int, fractions: list[float]) -> list[int]:
     """Ranks of fock_basis(m, n) at which the cumulative work of the multiplicity-aware permanent walk reaches the
     given fractions of the total (ascending, in [0, 1]); bisection on the exact cumulative work function (host
-    integer arithmetic, no device needed).  Below n = 7 the expanded-row kernel runs: uniform cost per state."""
+    integer arithmetic, no device needed).  Outside 7 <= n <= 16 the expanded-row kernel runs: uniform cost per state.
+    This is the readable statement of the arithmetic; the product path uses its C++ form lwb_shard_cuts
+    (csrc/comm.cu), and tests/test_abi_and_host.py compares the two cut for cut."""
     from math import comb
 
     total = comb(m + n - 1, n)
-    if n < 7:
+    if n < 7 or n > 16 or total >= 2 ** 32:  # the multiplicity-aware walk covers 7 <= n <= 16 and < 2^32 states
         return [min(total, max(0, int(round(total * f)))) for f in fractions]
     w_total = cumulative_work(m, n, total, STATE_OVERHEAD_TERMS)
     cuts = []

@@ -48,6 +48,14 @@ def test_compute_calls_fail_loudly_without_gpu():
         lb.PermanentBackend().sample_outputs(circ, [1, 0], 10, seed=1)
     with pytest.raises(lb.BackendError):
         lb.pdist_calc(circ, {(1, 0): 1.0}, lb.SLOSBackend())
+    with pytest.raises(lb.BackendError):  # nor behind the multi-GPU entry points
+        lb.Comm.local(2)
+    lb.set_n_gpus(2)
+    try:
+        with pytest.raises(lb.BackendError):
+            lb.PermanentBackend().full_probability_distribution(lb.CompiledCircuitView(np.eye(8)), [1] * 7 + [0])
+    finally:
+        lb.set_n_gpus(1)
 
 
 def test_keyspace_layout_host():
@@ -179,6 +187,21 @@ def test_cumulative_work_is_exact_and_cuts_balance():
         c0 = sharding.STATE_OVERHEAD_TERMS
         w = [sharding.cumulative_work(m, n, b, c0) - sharding.cumulative_work(m, n, a, c0) for a, b in ranges]
         assert max(w) / (sum(w) / world) < 1.0001
+
+
+def test_native_shard_cuts_equal_the_python_statement():
+    """lwb_shard_cuts (csrc/comm.cu, what the communicators use) against lightworks_b200.sharding.work_cuts, the
+    readable statement of the same exact-integer arithmetic: identical cuts, including piece fractions."""
+    from lightworks_b200 import sharding
+
+    for m, n, world in [(24, 10, 8), (16, 8, 4), (20, 12, 8), (12, 7, 3), (9, 7, 5), (18, 14, 8), (6, 3, 4),
+                        (30, 16, 8), (24, 10, 2), (40, 20, 8), (10, 9, 7)]:
+        fr = [k / world for k in range(world + 1)]
+        assert lb.shard_cuts(m, n, fr) == sharding.work_cuts(m, n, fr), (m, n, world)
+    fr = [(r + a) / 8 for r in range(8) for a in (0.0, 0.6, 0.9)] + [1.0]
+    assert lb.shard_cuts(24, 10, fr) == sharding.work_cuts(24, 10, fr)
+    with pytest.raises(ValueError):
+        lb.shard_cuts(200, 10, [0.0, 1.0])
 
 
 @pytest.mark.reference

@@ -47,6 +47,9 @@ class _FakeCtx:
     def dist_from_dense(self, n_modes, kmax, dense):
         return _FakeDist(n_modes, kmax, dense)
 
+    def dists_from_circuit(self, U_full, n_modes, in_states, threshold, backend, dtype, comm=None):  # noqa: N803
+        return [self.dist_from_circuit(U_full, n_modes, s, threshold, backend, dtype) for s in in_states]
+
     def dist_from_circuit(self, U_full, n_modes, in_state, threshold, backend, dtype):  # noqa: N803
         fn = O.pdist_permanent if backend == _lib.BACKEND_PERMANENT else O.pdist_slos
         keys, vals = fn(U_full, n_modes, list(in_state), threshold)

@@ -6,6 +6,13 @@ GPU parity tests: the CUDA path (through the C ABI, lightworks_b200._lib / backe
 plus size-independent properties at BASELINE.json's full sizes.
 Tolerances (BASELINE.json north_star): probabilities/amplitudes rel 1e-10 in complex128 and 1e-4 in
 complex64; Fock enumeration and state order bit-exact.
+
+Accuracy yardstick for n >= 16 (profiles/r02_accuracy_probe.log): the reference's algorithm (thewalrus perm_bbfg,
+restated in oracle/lw_oracle.c) updates its column sums incrementally over all 2^(n-1) Gray steps in double precision
+and is itself only accurate to 2.5e-13 (n=16), 3e-12 (n=20), 2e-11 (n=24), 2e-10 (n=26) relative to the exact permanent.
+The CUDA kernels restart from a fresh vector per chunk and stay below 2e-12 up to n=28.  The tests therefore hold the
+GPU to 1e-10 against the extended-precision adjudicator oracle.perm_hp (long double, compensated) at EVERY size, and to
+1e-10 against the reference algorithm wherever that algorithm is itself good to 1e-11.
 """
 import numpy as np
 import pytest
@@ -18,6 +25,14 @@ pytestmark = pytest.mark.gpu
 G = golden()
 REL128 = 1e-10
 REL64 = 1e-4
+
+
+def assert_perm_parity(got, A, rel=REL128, ref=None):  # noqa: N803
+    """got vs the adjudicator at `rel`; vs the reference algorithm at `rel` where that algorithm is accurate to rel/10."""
+    hp = O.perm_hp(A)
+    assert abs(got - hp) <= rel * abs(hp), (abs(got - hp) / abs(hp), A.shape)
+    if ref is not None and abs(ref - hp) <= 0.1 * rel * abs(hp):
+        assert abs(got - ref) <= rel * abs(ref), (abs(got - ref) / abs(ref), A.shape)
 
 
 @pytest.fixture(scope="module")
@@ -71,7 +86,7 @@ def test_pdist_literal_both_backends(lb):
         d = cls().full_probability_distribution(circ, lb.State([1, 1, 0]))
         assert len(d) == 6
         for k, v in d.items():
-            assert lit["pdist"][str(k.s)] == pytest.approx(v, 1e-8)
+            assert lit["pdist"][str(k.s)] == pytest.approx(v, 1e-8)  # the reference's own literal precision
 
 
 # ---------------------------------------------------------------- recorded reference calls
@@ -164,9 +179,15 @@ def test_perm_matrices_vs_oracle(ctx, n):
     A[0] = rng.normal(size=(n, n)) + 1j * rng.normal(size=(n, n))
     ref = O.perm_batch(A, threads=8)
     got = ctx.perm_matrices(A)
-    assert rel_close(got, ref, REL128 if n < 20 else 1e-9), n
-    if n <= 12:
-        assert rel_close(ctx.perm_matrices(A, dtype=1), ref, REL64, 1e-7), n
+    if n < 16:
+        assert rel_close(got, ref, REL128), n
+    else:
+        for b in range(B):
+            assert_perm_parity(got[b], A[b], ref=ref[b])
+    # complex64 variant at every size (restarts every 2^9 Gray steps + double accumulators keep it inside 1e-4)
+    got64 = ctx.perm_matrices(A, dtype=1)
+    scale = np.abs(A).max(axis=(1, 2)) ** n  # a permanent that cancels to ~0 is compared on the scale of its terms
+    assert np.all(np.abs(got64 - ref) <= REL64 * np.abs(ref) + 1e-7 * scale), n
 
 
 def test_perm_matrices_edge_shapes(ctx):
@@ -199,7 +220,7 @@ def test_basis_probs_vs_oracle(ctx, lb, m, n, seed):
     full = ctx.perm_basis_probs(U, ins)
     assert abs(full.sum() - 1) < 1e-10  # unitarity: the distribution is normalised
     slos = ctx.slos_basis_probs(U, ins, order=0)
-    assert rel_close(slos, full, 1e-9, 1e-15)  # independent algorithm, same numbers
+    assert rel_close(slos, full, REL128, 1e-18)  # independent algorithm, same numbers
 
 
 def test_golden_c3_c4_samples(ctx, lb):
@@ -214,15 +235,21 @@ def test_golden_c3_c4_samples(ctx, lb):
             assert p == pytest.approx(abs(a) ** 2, rel=REL128, abs=1e-20)
 
 
-@pytest.mark.parametrize("n", [2, 3, 5, 8, 12, 16, 20, 22])
+@pytest.mark.parametrize("n", [2, 3, 5, 8, 12, 16, 20, 22, 24, 26, 28])
 def test_perm_single_vs_oracle(ctx, n):
+    """BASELINE config 5 at its own sizes: U60[:n,:n], n = 20..28, against the oracle."""
     A = O.random_unitary(60, 5)[:n, :n]  # noqa: N806  (C5 input, SURVEY.md 8d)
-    ref = O.perm(A)
-    assert abs(ctx.perm_single(A) - ref) <= 1e-9 * abs(ref)
-    parts = sum(ctx.perm_single(A, slice_=s, n_slices=3) for s in range(3))  # multi-GPU Gray slices
-    assert abs(parts - ref) <= 1e-9 * abs(ref)
+    ref = O.perm(A) if n <= 26 else None  # the reference loop needs ~2 s at n = 26, ~8 s at n = 28
+    assert_perm_parity(ctx.perm_single(A), A, ref=ref)
+    for world in (3, 8):  # multi-GPU Gray slices
+        parts = sum(ctx.perm_single(A, slice_=s, n_slices=world) for s in range(world))
+        assert_perm_parity(parts, A, ref=ref)
     if n <= 20:
-        assert abs(ctx.perm_matrices(A[None])[0] - ref) <= 1e-9 * abs(ref)
+        assert_perm_parity(ctx.perm_matrices(A[None])[0], A, ref=ref)
+    # complex64 variant of the single-permanent kernel
+    hp = O.perm_hp(A)
+    assert abs(ctx.perm_single(A, dtype=1) - hp) <= REL64 * abs(hp)
+    assert abs(sum(ctx.perm_single(A, dtype=1, slice_=s, n_slices=4) for s in range(4)) - hp) <= REL64 * abs(hp)
 
 
 def test_perm_single_large_consistency(ctx):
@@ -236,7 +263,7 @@ def test_perm_single_large_consistency(ctx):
     A2[0] = U[31, :26]
     A[0] = A1[0] + A2[0]
     p, p1, p2 = ctx.perm_single(A), ctx.perm_single(A1), ctx.perm_single(A2)
-    assert abs(p - (p1 + p2)) <= 1e-9 * (abs(p1) + abs(p2))
+    assert abs(p - (p1 + p2)) <= REL128 * (abs(p1) + abs(p2))
 
 
 # ---------------------------------------------------------------- full-size properties (BASELINE configs)
@@ -257,12 +284,21 @@ def test_c3_full_distribution_properties(ctx, lb):
         ctx.perm_basis_probs_dev(dU, 24, dins, 10, 0, S, dp)
         ctx.slos_basis_probs_dev(dU, 24, ins, ds, order=0)
         torch.cuda.synchronize()
-        assert abs(float(dp.sum()) - 1.0) < 1e-9
-        assert abs(float(ds.sum()) - 1.0) < 1e-9
+        assert abs(float(dp.sum()) - 1.0) < 1e-12
+        assert abs(float(ds.sum()) - 1.0) < 1e-12
         err = (dp - ds).abs()
         big = dp > 1e-12
-        assert float((err[big] / dp[big]).max()) < 1e-8
-        assert float(err.max()) < 1e-17
+        assert float((err[big] / dp[big]).max()) < REL128  # measured 2.4e-12 (profiles/r02_accuracy_probe.log)
+        assert float(err.max()) < 1e-19
+        # complex64 variant on a 2 M-state slice of C3: 1e-4 on every state with p > 1e-7 (SURVEY.md 8d gate)
+        c0, cn = 10_000_000, 2_000_000
+        d64 = torch.empty(cn, dtype=torch.float64, device="cuda")
+        ctx.perm_basis_probs_dev(dU, 24, dins, 10, c0, cn, d64, dtype=1)
+        torch.cuda.synchronize()
+        ref64 = dp[c0:c0 + cn]
+        k64 = ref64 > 1e-7
+        assert float(((d64 - ref64).abs()[k64] / ref64[k64]).max()) < REL64
+        assert float((d64 - ref64).abs().max()) < 1e-10
         # shard 5 of 8
         r0, r1 = S * 5 // 8, S * 6 // 8
         shard = torch.empty(r1 - r0, dtype=torch.float64, device="cuda")
@@ -328,8 +364,8 @@ def test_c4_noise_model_hot_path_properties(ctx, lb):
         assert abs(p.sum() - 1) < 1e-10
         s = ctx.slos_basis_probs(U, ins, order=0)
         big = p > 1e-12
-        assert rel_close(s[big], p[big], 1e-8)
-        assert np.max(np.abs(s - p)) < 1e-16
+        assert rel_close(s[big], p[big], REL128)
+        assert np.max(np.abs(s - p)) < 1e-17
         keys, vals = ctx.pdist(U, 16, ins, 1e-9, 0)
         keep = p > 1e-9
         assert np.array_equal(vals, p[keep])
@@ -348,4 +384,5 @@ def test_c5_single_permanent_slices_n28(ctx):
     # scaling a row by c scales the permanent by c (size-independent property)
     B = A.copy()  # noqa: N806
     B[3] *= (0.5 - 2j)
-    assert abs(ctx.perm_single(B) - whole * (0.5 - 2j)) <= 1e-9 * abs(whole) * 2.1
+    assert abs(ctx.perm_single(B) - whole * (0.5 - 2j)) <= REL128 * abs(whole) * 2.1
+    assert abs(ctx.perm_single(A, dtype=1) - whole) <= REL64 * abs(whole)

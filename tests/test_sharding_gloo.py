@@ -95,3 +95,43 @@ def test_equal_work_pieces_pipeline_gloo():
         ret = mgr.dict()
         mp.spawn(_piece_worker, args=(world, port, ret), nprocs=world, join=True)
         assert all(ret[r] for r in range(world))
+
+
+def _native_cuts_worker(rank, world, port, ret):
+    """The product's multi-GPU step on gloo: shard boundaries from the C ABI (lwb_shard_cuts, what lwb_comm_* uses on
+    a GPU box), every rank writes its shard into ITS slice of a contiguous S-long buffer, the exchange leaves every
+    rank with the whole distribution in fock_basis order, and the all-reduced shard sums give the normalisation."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import lightworks_b200 as lb
+    from oracle import oracle as O  # noqa: N812
+
+    m, n = 9, 7
+    U = O.random_unitary(m, 4)  # noqa: N806
+    ins = [1] * n + [0] * (m - n)
+    S = O.fock_count(m, n)  # noqa: N806
+    cuts = lb.shard_cuts(m, n, [k / world for k in range(world + 1)])
+    full = torch.zeros(S, dtype=torch.float64)
+    a, b = cuts[rank], cuts[rank + 1]
+    full[a:b] = torch.from_numpy(O.basis_probabilities(U, ins, a, b - a))  # the device kernels on a GPU box
+    total = full[a:b].sum().reshape(1).clone()
+    for r in range(world):  # in-place broadcasts of unequal length = the NCCL fallback of lwb_comm_perm_basis_probs_dev
+        dist.broadcast(full[cuts[r]:cuts[r + 1]], src=r)
+    dist.all_reduce(total)
+    ref = O.basis_probabilities(U, ins)
+    ok = (np.array_equal(full.numpy(), ref) and abs(float(total) - 1.0) < 1e-12 and cuts[0] == 0 and cuts[-1] == S
+          and (cuts[1] - cuts[0]) != (cuts[2] - cuts[1]))  # equal work, not equal counts
+    dist.barrier()
+    dist.destroy_process_group()
+    ret[rank] = ok
+
+
+@pytest.mark.timeout(180)
+def test_native_shard_cuts_contiguous_gather_gloo():
+    world = 2
+    port = 33500 + os.getpid() % 2000
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_native_cuts_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert all(ret[r] for r in range(world))
