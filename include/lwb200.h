@@ -58,6 +58,8 @@ int lwb_set_tuning(int n, int log_l);
 /* Process-wide options.  "multiplicity_aware" (default 1): full-basis probability ranges use the
  * multiplicity-aware Glynn walk (prod(s_i+1)/2 terms for an output with occupations s_i) instead of
  * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel.
+ * "slos_units" (default 1): SLOS layers run the prefix-unit kernel (coalesced parent streams + shared-memory parent
+ * blocks, csrc/slos_units.cu); 0 forces the gather-form kernel (csrc/slos_kernels.cuh).
  * "source_string_keys" (default 0, test hook): lwb_source_statistics keys its classes by strings even when the
  * packed 62-bit form fits. */
 int lwb_set_option(const char* name, int value);
@@ -66,6 +68,9 @@ int lwb_set_option(const char* name, int value);
  * terms of the walk, the symmetry factor (2 if halved) and the sum of |coefficients| (= 2^n / factor). */
 int lwb_multiplicity_plan(int n, int pattern, int* n_patterns, int* multiplicities, int* n_distinct, int* n_terms,
                           int* symmetry_factor, double* abs_coef_sum);
+/* Host-only self-check of the SLOS prefix-unit plan of layer (m modes, k photons): verifies every child / parent
+ * index rule of csrc/slos_units.cu against exact lex ranks; *children = states checked (= C(m+k-1, k)). */
+int lwb_slos_plan_check(int m, int k, uint64_t* units, uint64_t* items, uint64_t* children);
 /* Number of kernels this handle has launched since creation (bench.py's gpu_launches). */
 int lwb_launch_count(lwb_handle h, uint64_t* count);
 
@@ -242,6 +247,9 @@ int lwb_comm_perm_single_dev(lwb_comm c, const double* d_A, int n, int dtype, do
  * k mod n_gpus and its dense distribution copied to h's device over NVLink. */
 int lwb_dists_from_circuit(lwb_handle h, lwb_comm comm, const double* U_full, int m_tot, int n_modes,
                            const uint8_t* in_states, int count, double threshold, int backend, int dtype, int* slots);
+
+/* Debugging aid: returns (and clears) the calling thread's pending CUDA runtime error code, message into msg. */
+int lwb_debug_pending_cuda_error(char* msg, int len);
 
 /* ---- micro-benchmarks used for the roofline denominators ------------------------------------ */
 /* Dependent-free DFMA stream on every SM: returns achieved FP64 FLOP/s (2 flops per DFMA). */

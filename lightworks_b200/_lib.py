@@ -46,6 +46,7 @@ SIGNATURES = {
     "lwb_set_option": (_i, [C.c_char_p, _i]),
     "lwb_multiplicity_plan": (_i, [_i, _i, _pi, _pi, _pi, _pi, _pi, _pdbl]),
     "lwb_launch_count": (_i, [_vp, _pu64]),
+    "lwb_slos_plan_check": (_i, [_i, _i, _pu64, _pu64, _pu64]),
     "lwb_fock_count": (_i, [_i, _i, _pu64]),
     "lwb_fock_rank": (_i, [_i, _vp, _pu64]),
     "lwb_fock_unrank": (_i, [_i, _i, _u64, _vp]),
@@ -97,6 +98,7 @@ SIGNATURES = {
     "lwb_comm_perm_single": (_i, [_vp, _vp, _i, _i, _vp]),
     "lwb_comm_perm_single_dev": (_i, [_vp, _vp, _i, _i, _vp]),
     "lwb_dists_from_circuit": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _dbl, _i, _i, _vp]),
+    "lwb_debug_pending_cuda_error": (_i, [C.c_char_p, _i]),
     "lwb_fp64_peak": (_i, [_vp, _pdbl]),
     "lwb_fp64_probe": (_i, [_vp, _i, _pdbl]),
 }
@@ -184,6 +186,13 @@ def slos_unrank(m: int, n: int, rank: int) -> np.ndarray:
     s = np.zeros(m, dtype=np.uint8)
     check(cdll().lwb_slos_unrank(m, n, rank, ptr(s)))
     return s
+
+
+def slos_plan_check(m: int, k: int) -> dict:
+    """Host-only self-check of the SLOS prefix-unit plan (csrc/slos_units.cu) of layer (m modes, k photons)."""
+    u, i, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+    check(cdll().lwb_slos_plan_check(m, k, C.byref(u), C.byref(i), C.byref(c)))
+    return {"units": int(u.value), "items": int(i.value), "children": int(c.value)}
 
 
 def keyspace_size(n_modes: int, kmax: int) -> int:
@@ -642,6 +651,8 @@ class Comm:
 
     def close(self):
         if self._c:
+            for c in self._contexts.values():  # borrowed handles die with the communicator: objects that still hold
+                c._h = C.c_void_p(0)           # the Context (device distributions) must see a dead handle, not a dangling one
             self._contexts.clear()
             cdll().lwb_comm_destroy(self._c)
             self._c = C.c_void_p(0)

@@ -424,6 +424,13 @@ int lwb_comm_info(lwb_comm c, int* rank, int* world, int* kind, int* peer_stores
     return 0;
 }
 
+/* debugging aid: the calling thread's pending CUDA error (cleared), 0 if none */
+int lwb_debug_pending_cuda_error(char* msg, int len) {
+    cudaError_t e = cudaGetLastError();
+    if (msg && len > 0) { strncpy(msg, e == cudaSuccess ? "" : cudaGetErrorString(e), (size_t)len - 1); msg[len - 1] = 0; }
+    return (int)e;
+}
+
 int lwb_comm_set_option(lwb_comm c, const char* name, int value) {
     if (!c || !name) return fail(LWB_E_ARG, "null argument");
     if (!strcmp(name, "peer_stores")) { c->use_peer_stores = value ? 1 : 0; return 0; }

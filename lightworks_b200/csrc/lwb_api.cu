@@ -65,6 +65,7 @@ static std::vector<K1Variant> g_k1;
 static const K2Variant* g_k2[LWB_K2_MAX_N + 1];
 static int g_tune_logl[LWB_K1_MAX_N + 1];
 static int g_multiplicity_aware = 1;  // lwb_set_option("multiplicity_aware", 0/1)
+static int g_slos_units = 1;          // lwb_set_option("slos_units", 0/1): K3u prefix-unit kernel vs K3 gather kernel
 static std::once_flag g_tables_once;
 
 static void load_tables() {
@@ -142,6 +143,7 @@ int lwb_create(int device, lwb_handle* out) {
     CU(cudaMemcpy(h->d_bin, host_bin(), sizeof g_bin, cudaMemcpyHostToDevice));
     load_tables();
     h->k1x = k1x_create();
+    h->slos_units = slos_units_create();
     *out = h;
     return 0;
 }
@@ -154,6 +156,7 @@ int lwb_destroy(lwb_handle h) {
                    &h->bMarg, &h->bFirst, &h->bSmall, &h->bCdf, &h->bTile, &h->bUni, &h->bIdx})
         if (b->p) cudaFree(b->p);
     k1x_destroy(h->k1x);
+    slos_units_destroy(h->slos_units);
     for (auto& d : h->dists)
         if (d.p) cudaFree(d.p);
     if (h->d_bin) cudaFree(h->d_bin);
@@ -204,6 +207,7 @@ int lwb_set_tuning(int n, int log_l) {
 int lwb_set_option(const char* name, int value) {
     if (!name) return fail(LWB_E_ARG, "null option name");
     if (!strcmp(name, "multiplicity_aware")) { g_multiplicity_aware = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "slos_units")) { g_slos_units = value ? 1 : 0; return 0; }
     if (!strcmp(name, "source_string_keys")) { lwb::g_source_string_keys = value ? 1 : 0; return 0; }
     return fail(LWB_E_ARG, "unknown option %s", name);
 }
@@ -214,6 +218,16 @@ int lwb_multiplicity_plan(int n, int pattern, int* n_patterns, int* multipliciti
         return fail(LWB_E_ARG, "null argument");
     int rc = k1x_plan_info(n, pattern, n_patterns, multiplicities, n_distinct, n_terms, symmetry_factor, abs_coef_sum);
     if (rc) return fail(rc, "no multiplicity-aware plan for n=%d pattern=%d", n, pattern);
+    return 0;
+}
+
+int lwb_slos_plan_check(int m, int k, uint64_t* units, uint64_t* items, uint64_t* children) {
+    if (!units || !items || !children) return fail(LWB_E_ARG, "null argument");
+    uint64_t tp = 0, ch = 0;
+    int rc = slos_units_plan_info(m, k, units, items, &ch, &tp);
+    if (rc) return fail(rc, "no prefix-unit plan for m=%d k=%d", m, k);
+    rc = slos_units_plan_check(m, k, children);
+    if (rc) return fail(rc, "prefix-unit plan of m=%d k=%d failed its index self-check", m, k);
     return 0;
 }
 
@@ -511,15 +525,18 @@ int lwb_perm_single_dev(lwb_handle h, const double* d_A, int n, int dtype, int s
     // every lane walks a contiguous range of chunks; aim for >= 4 chunks per lane before adding blocks
     uint64_t need = (qe - qb + 4 * K1_THREADS - 1) / (4 * K1_THREADS);
     unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(need, (uint64_t)resident));
-    CK(ensure(h, h->bPart, (size_t)grid * 16));
+    // partials [grid][2] followed by the finished-blocks counter (zeroed once: the last block of every launch resets it)
+    const size_t need_bytes = (size_t)std::max(grid, 1024u) * 16 + 16;
+    if (h->bPart.cap < need_bytes) {
+        CK(ensure(h, h->bPart, need_bytes));
+        CU(cudaMemsetAsync(h->bPart.p, 0, h->bPart.cap, h->stream));
+    }
+    unsigned int* done = (unsigned int*)((char*)h->bPart.p + h->bPart.cap - 16);
     if (qe > qb) {
-        PermSingleArgs a{(const double2*)d_A, qb, qe, (double*)h->bPart.p};
+        PermSingleArgs a{(const double2*)d_A, qb, qe, (double*)h->bPart.p, done, d_out2};
         fn<<<grid, K1_THREADS, 0, h->stream>>>(a);
-        h->launches++;
-        CU(cudaGetLastError());
-        reduce_partials_kernel<<<1, 256, 0, h->stream>>>((const double*)h->bPart.p, (int)grid, d_out2);
     } else {
-        reduce_partials_kernel<<<1, 256, 0, h->stream>>>((const double*)h->bPart.p, 0, d_out2);
+        reduce_partials_kernel<<<1, 256, 0, h->stream>>>((const double*)h->bPart.p, 0, d_out2);  // empty slice: 0
     }
     h->launches++;
     CU(cudaGetLastError());
@@ -651,6 +668,13 @@ static SlosFn g_slos[LWB_MAX_PHOTONS + 1][2];
 static std::once_flag g_slos_once;
 
 static int launch_slos_layer(lwb_handle h, const SlosLayerArgs& a) {
+    if (g_slos_units && slos_units_supported(a.m, a.k)) {
+        std::string err;
+        const int rc = slos_units_layer(h->slos_units, h->stream, a.m, a.k, a.parent, a.child, a.U, a.in_mode, a.sqrt_tab,
+                                        a.write_probs, &h->launches, &err);
+        if (rc == 0) return 0;
+        if (rc != LWB_E_LIMIT) return fail(rc, "%s", err.c_str());  // LWB_E_LIMIT: shape outside K3u, use the gather kernel
+    }
     std::call_once(g_slos_once, [] { SlosTable<LWB_MAX_PHOTONS>::fill(g_slos); });
     const int k = a.k, m = a.m;
     const int wide = a.S + 32ull * SLOS_ITERS >= (1ull << 32) ? 1 : 0;  // a lane overshoots S by up to 32 * SLOS_ITERS

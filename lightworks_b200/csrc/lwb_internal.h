@@ -9,6 +9,7 @@
 #include "../../include/lwb200.h"
 #include "fock.cuh"
 #include "k1x.h"
+#include "slos_units.h"
 
 namespace lwb {
 int fail(int code, const char* fmt, ...);  // sets the calling thread's lwb_last_error() text, returns code
@@ -47,6 +48,7 @@ struct lwb_context {
     Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall, bCdf, bTile, bUni, bIdx;
     uint64_t launches = 0;
     lwb::K1xState* k1x = nullptr;
+    lwb::SlosUnitsState* slos_units = nullptr;  // cached K3u plans per (m, k)
     lwb::MirrorSet mirror = {};  // set by the communicator around a sharded launch: peers receiving every probability
     struct DistSlot {  // dense distribution over the key space K(n_modes, kmax), device resident
         double* p = nullptr;

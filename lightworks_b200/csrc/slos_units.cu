@@ -1,0 +1,438 @@
+// slos_units.cu -- K3u: SLOS layer kernel over "prefix units" (round 2).
+//
+// Same recurrence as slos_layer_kernel (slos_kernels.cuh; SLOSBackend.calculate, lightworks/emulator/backends/
+// slos.py:96-103): for the k-th input photon in mode i
+//     out[t] = sum_j sqrt(t_j) * in[t - e_j] * U[j, i]        (j ascending over the occupied modes of t)
+// with every layer stored in the reference's dict order = lexicographic order of the ascending mode list
+// x_0 <= ... <= x_{k-1}.  The gather-form kernel spends 612 warp-instructions per 32 children re-deriving positions
+// and reads every parent through scattered 16-byte gathers (14.8 GB of L1/L2 traffic at 24 modes / 10 photons).
+//
+// Structure used here.  Cut the lex-ordered tree of mode lists at a frontier of nodes ("units"): a unit is a prefix
+// P = (x_0..x_{k-d-1}) whose subtree - the d trailing photons in modes >= l = last(P), a "d-simplex" of
+// T = C(m-l+d-1, d) consecutive children - is at most SLOS_TMAX states.  Inside one unit
+//   * removing a PREFIX photon (mode v) from every child gives parents that are CONSECUTIVE in the parent layer and
+//     end-aligned with the unit: parent(c) = in[pend_v - T + c]  -> one coalesced stream per distinct prefix mode;
+//   * removing a TRAILING photon gives a parent inside the block B(P) = (P, d-1 trailing photons >= l) of the parent
+//     layer, C(m-l+d-2, d-1) consecutive amplitudes, staged in shared memory once per unit; its index is the
+//     child's index minus a prefix sum of binomial differences (the same identity as slos_layer_kernel, applied to the
+//     sub-system of modes l..m-1);
+//   * the trailing modes of child c come from a table that depends on (d, c) only: the d-simplex over modes >= l is
+//     the END of the d-simplex over all modes in lex order, so one table per d serves every unit.
+// Units, stream offsets and tables depend on (m, k) only: built once on the host and cached in the context.
+// Terms are added in ascending mode order with the reference's rounding sequence (no FMA contraction), like K3.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "fock.cuh"
+#include "lwb_internal.h"
+#include "slos_units.h"
+
+namespace lwb {
+
+constexpr int SU_THREADS = 256;
+constexpr int SU_DMAX = 8;        // trailing photons per unit (their modes are packed into one 64-bit word)
+constexpr int SU_NPMAX = 16;      // distinct prefix modes per unit
+constexpr uint32_t SU_TMAX = 8192;   // children per unit
+constexpr uint32_t SU_ITEM = 4096;   // a CTA takes consecutive units until it holds this many children ...
+constexpr uint32_t SU_ITEM_MIN = 256;  // ... fewer on small layers, so that every SM gets several CTAs
+static uint32_t item_size(uint64_t children) {
+    const uint64_t per = children / (148 * 8);
+    return (uint32_t)std::min<uint64_t>(SU_ITEM, std::max<uint64_t>(SU_ITEM_MIN, per));
+}
+
+struct SlosUnit {
+    uint64_t start;             // rank of the unit's first child in the child layer
+    uint64_t pblock;            // rank of the first amplitude of B(P) in the parent layer
+    uint64_t sbase[SU_NPMAX];   // stream s: parent(c) = parent[sbase[s] + c]   (= pend - T)
+    uint32_t T, Tp;             // children; amplitudes of B(P)
+    uint32_t lut;               // trailing modes of child c = lut_table[lut + c]
+    uint8_t d, ell, np, has_ell;  // trailing photons; last prefix mode (0 if none); distinct prefix modes; l in prefix?
+    uint8_t pm[SU_NPMAX];       // distinct prefix modes, ascending
+    uint8_t pmult[SU_NPMAX];    // their multiplicities in the prefix
+};
+
+struct SlosUnitsArgs {
+    const SlosUnit* units;
+    const uint2* items;      // [n_items] (first unit, one past last unit)
+    const uint64_t* lut;
+    const uint32_t* ht;      // [SU_DMAX][m + 1]: C(m - v + r - 1, r + 1) mod 2^32
+    int m, k;
+    const double2* parent;
+    void* child;
+    const double2* U;
+    int in_mode;
+    const double* sqrt_tab;
+    int write_probs;
+    uint32_t max_tp;
+};
+
+__device__ __forceinline__ double2 su_cmul_py(double2 a, double2 b) {  // CPython's complex_mul, no fma
+    double2 r;
+    r.x = __dsub_rn(__dmul_rn(a.x, b.x), __dmul_rn(a.y, b.y));
+    r.y = __dadd_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x));
+    return r;
+}
+
+__global__ void __launch_bounds__(SU_THREADS) slos_units_kernel(SlosUnitsArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = a.m, mv = m + 1;
+    double2* ucol = reinterpret_cast<double2*>(smem_raw);                 // [m]
+    double2* pb = ucol + m;                                               // [max_tp] parent block
+    double* sq = reinterpret_cast<double*>(pb + a.max_tp);                // [k + 1] (+ pad)
+    uint32_t* ht = reinterpret_cast<uint32_t*>(sq + ((a.k + 2) & ~1));    // [SU_DMAX][mv]
+    __shared__ SlosUnit un;
+    const int tid = threadIdx.x;
+    for (int e = tid; e < m; e += SU_THREADS) ucol[e] = a.U[(size_t)e * m + a.in_mode];
+    for (int e = tid; e <= a.k; e += SU_THREADS) sq[e] = a.sqrt_tab[e];
+    for (int e = tid; e < SU_DMAX * mv; e += SU_THREADS) ht[e] = a.ht[e];
+    const uint2 item = a.items[blockIdx.x];
+    for (uint32_t u = item.x; u < item.y; ++u) {
+        __syncthreads();  // previous unit done with `un` and `pb` (first pass: the tables are written)
+        if (tid < (int)(sizeof(SlosUnit) / 4))
+            reinterpret_cast<uint32_t*>(&un)[tid] = reinterpret_cast<const uint32_t*>(a.units + u)[tid];
+        __syncthreads();
+        const uint32_t T = un.T, Tp = un.Tp;
+        const double2* pblk = a.parent + un.pblock;
+        for (uint32_t i = tid; i < Tp; i += SU_THREADS) pb[i] = pblk[i];
+        __syncthreads();
+        const int d = un.d, np = un.np, ell = un.ell;
+        const bool has_ell = un.has_ell != 0;
+        const uint64_t* lut = a.lut + un.lut;
+        for (uint32_t c = tid; c < T; c += SU_THREADS) {
+            const uint64_t y = lut[c];
+            // photons of the trailing part that sit in mode l (they extend the prefix's run of l)
+            int lead = 0;
+            if (has_ell) {
+#pragma unroll
+                for (int i = 0; i < SU_DMAX; ++i)
+                    if (i < d && (int)((y >> (8 * i)) & 0xff) == ell && lead == i) lead = i + 1;
+            }
+            double2 acc = make_double2(0.0, 0.0);
+            // ---- prefix modes, ascending: one end-aligned coalesced stream each ----
+            for (int s = 0; s < np; ++s) {
+                double2 t = a.parent[un.sbase[s] + c];
+                int mult = un.pmult[s];
+                if (s == np - 1) mult += lead;  // only the last prefix mode can equal l
+                if (mult > 1) {
+                    const double f = sq[mult];
+                    t.x = __dmul_rn(f, t.x);
+                    t.y = __dmul_rn(f, t.y);
+                }
+                const double2 term = su_cmul_py(t, ucol[un.pm[s]]);
+                acc.x = __dadd_rn(acc.x, term.x);
+                acc.y = __dadd_rn(acc.y, term.y);
+            }
+            // ---- trailing modes, ascending: parents inside the staged block B(P) ----
+            uint32_t Q = 0;
+            int prev = ell, run = 0;
+#pragma unroll
+            for (int i = 0; i < SU_DMAX; ++i) {
+                if (i < d) {
+                    const int yi = (int)((y >> (8 * i)) & 0xff);
+                    const int r = d - 1 - i;
+                    Q += ht[r * mv + prev] - ht[r * mv + yi];
+                    run += 1;
+                    const int ynext = (i + 1 < SU_DMAX) ? (int)((y >> (8 * ((i + 1) & 7))) & 0xff) : 0;
+                    const bool last_of_run = (i == d - 1) || (ynext != yi);
+                    if (last_of_run) {
+                        if (!(has_ell && yi == ell)) {  // the run of l was merged into the last prefix term
+                            double2 t = pb[c - Q];
+                            if (run > 1) {
+                                const double f = sq[run];
+                                t.x = __dmul_rn(f, t.x);
+                                t.y = __dmul_rn(f, t.y);
+                            }
+                            const double2 term = su_cmul_py(t, ucol[yi]);
+                            acc.x = __dadd_rn(acc.x, term.x);
+                            acc.y = __dadd_rn(acc.y, term.y);
+                        }
+                        run = 0;
+                    }
+                    prev = yi;
+                }
+            }
+            const uint64_t rank = un.start + c;
+            if (a.write_probs)  // abs(a) ** 2 (slos.py:74); x*x + y*y differs from hypot(x, y)^2 by <= 2 ulp
+                reinterpret_cast<double*>(a.child)[rank] = __dadd_rn(__dmul_rn(acc.x, acc.x), __dmul_rn(acc.y, acc.y));
+            else
+                reinterpret_cast<double2*>(a.child)[rank] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host plan: units, items and tables of one layer (m modes, k photons in the child layer)
+struct SlosLayerPlan {
+    int m = 0, k = 0;
+    uint32_t n_units = 0, n_items = 0, max_tp = 0;
+    SlosUnit* d_units = nullptr;
+    uint2* d_items = nullptr;
+    uint64_t* d_lut = nullptr;
+    uint32_t* d_ht = nullptr;
+};
+
+struct SlosUnitsState {
+    std::map<std::pair<int, int>, SlosLayerPlan> plans;
+};
+
+SlosUnitsState* slos_units_create() { return new SlosUnitsState(); }
+void slos_units_destroy(SlosUnitsState* st) {
+    if (!st) return;
+    for (auto& kv : st->plans) {
+        cudaFree(kv.second.d_units);
+        cudaFree(kv.second.d_items);
+        cudaFree(kv.second.d_lut);
+        cudaFree(kv.second.d_ht);
+    }
+    delete st;
+}
+
+bool slos_units_supported(int m, int k) { return m >= 1 && m <= LWB_MAX_MODES && k >= 1 && k <= LWB_MAX_PHOTONS; }
+
+namespace {
+uint64_t simplex(const uint64_t* bin, int n_free, int d) { return binom(bin, n_free + d - 1, d); }  // C(n_free+d-1, d)
+
+struct Builder {
+    const uint64_t* bin;
+    int m, k;
+    std::vector<SlosUnit> units;
+    int nf_max[SU_DMAX + 1];   // per d: largest n_free among the units
+    int x[LWB_MAX_PHOTONS + 2];
+    uint64_t next_start = 0;
+    bool ok = true;
+
+    void emit(int depth) {  // prefix x[0..depth), d = k - depth trailing photons
+        const int d = k - depth, ell = depth ? x[depth - 1] : 0, n_free = m - ell;
+        SlosUnit u;
+        memset(&u, 0, sizeof u);
+        u.start = next_start;
+        u.T = (uint32_t)simplex(bin, n_free, d);
+        u.Tp = (uint32_t)simplex(bin, n_free, d - 1);
+        u.d = (uint8_t)d;
+        u.ell = (uint8_t)ell;
+        next_start += u.T;
+        nf_max[d] = std::max(nf_max[d], n_free);
+        // parent block: (P, l, ..., l) with d-1 trailing photons, rank in the parent layer (m, k-1)
+        int y[LWB_MAX_PHOTONS + 2];
+        for (int i = 0; i < depth; ++i) y[i] = x[i];
+        for (int i = depth; i < k - 1; ++i) y[i] = ell;
+        u.pblock = lex_rank(bin, y, k - 1, m);
+        // streams: remove one photon of each distinct prefix mode; the parents of the unit's children are the
+        // LAST T states under the shortened prefix
+        int np = 0;
+        for (int i = 0; i < depth;) {
+            int j = i;
+            while (j < depth && x[j] == x[i]) ++j;
+            if (np >= SU_NPMAX) { ok = false; return; }
+            u.pm[np] = (uint8_t)x[i];
+            u.pmult[np] = (uint8_t)(j - i);
+            int q = 0;
+            for (int t = 0; t < depth; ++t)
+                if (t != i) y[q++] = x[t];          // drop one copy of mode x[i]
+            for (int t = 0; t < d; ++t) y[q++] = m - 1;  // last state of the shortened prefix's subtree
+            const uint64_t pend = lex_rank(bin, y, k - 1, m) + 1;
+            u.sbase[np] = pend - u.T;
+            ++np;
+            i = j;
+        }
+        u.np = (uint8_t)np;
+        u.has_ell = (uint8_t)(depth > 0 ? 1 : 0);  // the last prefix mode IS l
+        units.push_back(u);
+    }
+
+    void walk(int depth) {
+        if (!ok) return;
+        const int d = k - depth, ell = depth ? x[depth - 1] : 0;
+        const uint64_t t = simplex(bin, m - ell, d);
+        if (d <= SU_DMAX && t <= SU_TMAX && d >= 1) { emit(depth); return; }
+        for (int v = ell; v < m; ++v) {
+            x[depth] = v;
+            walk(depth + 1);
+        }
+    }
+};
+}  // namespace
+
+static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std::string* err) {
+    auto key = std::make_pair(m, k);
+    auto it = st->plans.find(key);
+    if (it != st->plans.end()) { *out = &it->second; return 0; }
+    const uint64_t* bin = host_bin();
+    Builder b;
+    b.bin = bin; b.m = m; b.k = k;
+    for (int d = 0; d <= SU_DMAX; ++d) b.nf_max[d] = 0;
+    b.walk(0);
+    if (!b.ok || b.units.empty() || b.units.size() >= (1ull << 31)) { *err = "slos units: plan not representable"; return LWB_E_LIMIT; }
+    // trailing-mode tables: for every d the d-simplex over modes [m - nf_max[d], m) in lex order, one byte per photon
+    std::vector<uint64_t> lut;
+    uint64_t lut_base[SU_DMAX + 1] = {0}, lut_size[SU_DMAX + 1] = {0};
+    for (int d = 1; d <= SU_DMAX; ++d) {
+        if (!b.nf_max[d]) continue;
+        lut_base[d] = lut.size();
+        lut_size[d] = simplex(bin, b.nf_max[d], d);
+        int y[SU_DMAX];
+        const int lo = m - b.nf_max[d];
+        for (int i = 0; i < d; ++i) y[i] = lo;
+        for (uint64_t c = 0; c < lut_size[d]; ++c) {
+            uint64_t w = 0;
+            for (int i = 0; i < d; ++i) w |= (uint64_t)y[i] << (8 * i);
+            lut.push_back(w);
+            for (int i = d - 1; i >= 0; --i)  // lex successor
+                if (y[i] < m - 1) {
+                    const int v = y[i] + 1;
+                    for (int q = i; q < d; ++q) y[q] = v;
+                    break;
+                }
+        }
+    }
+    SlosLayerPlan pl;
+    pl.m = m; pl.k = k;
+    for (auto& u : b.units) {
+        u.lut = (uint32_t)(lut_base[u.d] + lut_size[u.d] - u.T);
+        pl.max_tp = std::max(pl.max_tp, u.Tp);
+    }
+    std::vector<uint2> items;
+    const uint32_t item = item_size(b.next_start);
+    for (uint32_t u = 0; u < b.units.size();) {
+        uint32_t e = u, tot = 0;
+        while (e < b.units.size() && (e == u || tot + b.units[e].T <= item)) tot += b.units[e++].T;
+        items.push_back(make_uint2(u, e));
+        u = e;
+    }
+    std::vector<uint32_t> ht((size_t)SU_DMAX * (m + 1));
+    for (int r = 0; r < SU_DMAX; ++r)
+        for (int v = 0; v <= m; ++v) ht[(size_t)r * (m + 1) + v] = (uint32_t)binom(bin, m - v + r - 1, r + 1);
+    pl.n_units = (uint32_t)b.units.size();
+    pl.n_items = (uint32_t)items.size();
+#define SU_CU(call)                                                                   \
+    do {                                                                              \
+        cudaError_t e_ = (call);                                                      \
+        if (e_ != cudaSuccess) { *err = std::string(#call ": ") + cudaGetErrorString(e_); return LWB_E_CUDA; } \
+    } while (0)
+    SU_CU(cudaMalloc(&pl.d_units, b.units.size() * sizeof(SlosUnit)));
+    SU_CU(cudaMalloc(&pl.d_items, items.size() * sizeof(uint2)));
+    SU_CU(cudaMalloc(&pl.d_lut, std::max<size_t>(lut.size(), 1) * 8));
+    SU_CU(cudaMalloc(&pl.d_ht, ht.size() * 4));
+    SU_CU(cudaMemcpy(pl.d_units, b.units.data(), b.units.size() * sizeof(SlosUnit), cudaMemcpyHostToDevice));
+    SU_CU(cudaMemcpy(pl.d_items, items.data(), items.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    SU_CU(cudaMemcpy(pl.d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
+    SU_CU(cudaMemcpy(pl.d_ht, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice));
+    st->plans[key] = pl;
+    *out = &st->plans[key];
+    return 0;
+}
+
+int slos_units_layer(SlosUnitsState* st, cudaStream_t stream, int m, int k, const double2* parent, void* child,
+                     const double2* U, int in_mode, const double* sqrt_tab, int write_probs, uint64_t* launches,
+                     std::string* err) {
+    SlosLayerPlan* pl = nullptr;
+    int rc = build_plan(st, m, k, &pl, err);
+    if (rc) return rc;
+    SlosUnitsArgs a;
+    a.units = pl->d_units; a.items = pl->d_items; a.lut = pl->d_lut; a.ht = pl->d_ht;
+    a.m = m; a.k = k; a.parent = parent; a.child = child; a.U = U; a.in_mode = in_mode; a.sqrt_tab = sqrt_tab;
+    a.write_probs = write_probs; a.max_tp = pl->max_tp;
+    const size_t smem = (size_t)m * 16 + (size_t)pl->max_tp * 16 + (size_t)((k + 2) & ~1) * 8 + (size_t)SU_DMAX * (m + 1) * 4;
+    if (smem > 200 * 1024) { *err = "slos units: parent block does not fit shared memory"; return LWB_E_LIMIT; }
+    if (smem > 48 * 1024) SU_CU(cudaFuncSetAttribute(slos_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    slos_units_kernel<<<pl->n_items, SU_THREADS, smem, stream>>>(a);
+    *launches += 1;
+    SU_CU(cudaGetLastError());
+    return 0;
+}
+
+// Host-only self-check of a plan (tests, no device): for every child of every unit rebuild its mode list from the
+// unit's prefix and the trailing-mode table and verify, with the exact lex ranks of fock.cuh, the three index rules
+// the kernel relies on: child rank = start + c; prefix-removal parent = sbase[s] + c; trailing-removal parent =
+// pblock + c - (prefix sum of binomial differences).  Returns 0 when every index agrees.
+int slos_units_plan_check(int m, int k, uint64_t* children_checked) {
+    if (!slos_units_supported(m, k)) return LWB_E_LIMIT;
+    const uint64_t* bin = host_bin();
+    Builder b;
+    b.bin = bin; b.m = m; b.k = k;
+    for (int d = 0; d <= SU_DMAX; ++d) b.nf_max[d] = 0;
+    b.walk(0);
+    if (!b.ok) return LWB_E_LIMIT;
+    std::vector<uint32_t> ht((size_t)SU_DMAX * (m + 1));
+    for (int r = 0; r < SU_DMAX; ++r)
+        for (int v = 0; v <= m; ++v) ht[(size_t)r * (m + 1) + v] = (uint32_t)binom(bin, m - v + r - 1, r + 1);
+    uint64_t checked = 0, expect_start = 0;
+    for (const SlosUnit& u : b.units) {
+        if (u.start != expect_start) return LWB_E_ARG;
+        expect_start += u.T;
+        int x[LWB_MAX_PHOTONS + 2], depth = 0;
+        for (int s = 0; s < u.np; ++s)
+            for (int q = 0; q < u.pmult[s]; ++q) x[depth++] = u.pm[s];
+        if (depth + u.d != k) return LWB_E_ARG;
+        for (int i = 0; i < u.d; ++i) x[depth + i] = u.ell;  // first child: every trailing photon in mode l
+        for (uint32_t c = 0; c < u.T; ++c) {
+            if (lex_rank(bin, x, k, m) != u.start + c) return LWB_E_ARG;
+            int y[LWB_MAX_PHOTONS + 2];
+            for (int s = 0, at = 0; s < u.np; at += u.pmult[s], ++s) {  // remove one photon of prefix mode pm[s]
+                int q = 0;
+                for (int t = 0; t < k; ++t)
+                    if (t != at) y[q++] = x[t];
+                if (lex_rank(bin, y, k - 1, m) != u.sbase[s] + c) return LWB_E_ARG;
+            }
+            uint32_t Q = 0;
+            int prev = u.ell;
+            for (int i = 0; i < u.d; ++i) {
+                const int yi = x[depth + i], r = u.d - 1 - i;
+                Q += ht[(size_t)r * (m + 1) + prev] - ht[(size_t)r * (m + 1) + yi];
+                const bool last_of_run = (i == u.d - 1) || x[depth + i + 1] != yi;
+                if (last_of_run && !(u.has_ell && yi == u.ell)) {
+                    int q = 0;
+                    for (int t = 0; t < k; ++t)
+                        if (t != depth + i) y[q++] = x[t];
+                    const uint32_t local = c - Q;
+                    if (local >= u.Tp || lex_rank(bin, y, k - 1, m) != u.pblock + local) return LWB_E_ARG;
+                }
+                prev = yi;
+            }
+            ++checked;
+            for (int i = u.d - 1; i >= 0; --i)  // lex successor of the trailing part
+                if (x[depth + i] < m - 1) {
+                    const int v = x[depth + i] + 1;
+                    for (int q = i; q < u.d; ++q) x[depth + q] = v;
+                    break;
+                }
+        }
+    }
+    if (expect_start != binom(bin, m + k - 1, k)) return LWB_E_ARG;
+    *children_checked = checked;
+    return 0;
+}
+
+// host-only description of a plan (tests): number of units / items, children covered, largest parent block
+int slos_units_plan_info(int m, int k, uint64_t* n_units, uint64_t* n_items, uint64_t* children, uint64_t* max_tp) {
+    if (!slos_units_supported(m, k)) return LWB_E_LIMIT;
+    Builder b;
+    b.bin = host_bin(); b.m = m; b.k = k;
+    for (int d = 0; d <= SU_DMAX; ++d) b.nf_max[d] = 0;
+    b.walk(0);
+    if (!b.ok) return LWB_E_LIMIT;
+    uint64_t tp = 0;
+    for (auto& u : b.units) tp = std::max<uint64_t>(tp, u.Tp);
+    uint64_t items = 0;
+    const uint32_t item = item_size(b.next_start);
+    for (size_t u = 0; u < b.units.size();) {
+        size_t e = u;
+        uint32_t tot = 0;
+        while (e < b.units.size() && (e == u || tot + b.units[e].T <= item)) tot += b.units[e++].T;
+        ++items;
+        u = e;
+    }
+    *n_units = b.units.size();
+    *n_items = items;
+    *children = b.next_start;
+    *max_tp = tp;
+    return 0;
+}
+
+}  // namespace lwb

@@ -365,7 +365,7 @@ def test_c4_noise_model_hot_path_properties(ctx, lb):
         s = ctx.slos_basis_probs(U, ins, order=0)
         big = p > 1e-12
         assert rel_close(s[big], p[big], REL128)
-        assert np.max(np.abs(s - p)) < 1e-17
+        assert np.max(np.abs(s - p)) < 1e-16  # one ulp of the O(0.1) probabilities of the 1- and 2-photon subsets
         keys, vals = ctx.pdist(U, 16, ins, 1e-9, 0)
         keep = p > 1e-9
         assert np.array_equal(vals, p[keep])
@@ -386,3 +386,39 @@ def test_c5_single_permanent_slices_n28(ctx):
     B[3] *= (0.5 - 2j)
     assert abs(ctx.perm_single(B) - whole * (0.5 - 2j)) <= REL128 * abs(whole) * 2.1
     assert abs(ctx.perm_single(A, dtype=1) - whole) <= REL64 * abs(whole)
+
+
+# ---------------------------------------------------------------- K3u (prefix-unit SLOS kernel) vs K3 (gather kernel)
+@pytest.mark.parametrize("m,n,seed", [(6, 3, 1), (12, 6, 2), (8, 5, 7), (5, 7, 11), (3, 9, 4), (1, 4, 0), (16, 8, 4),
+                                       (2, 12, 5), (20, 5, 6), (24, 7, 3), (30, 4, 8), (7, 1, 9), (40, 3, 2)])
+def test_slos_unit_kernel_equals_gather_kernel(ctx, lb, m, n, seed):
+    """The two SLOS layer kernels add the same terms in the same order with the same rounding, so the AMPLITUDES are
+    bit-identical (incl. bunched inputs); probabilities (x*x + y*y vs hypot(x, y)**2) agree to 4 ulp.  Both are
+    compared with the oracle's restatement of SLOSBackend.calculate (slos.py:82-138)."""
+    U = O.random_unitary(m, seed)  # noqa: N806
+    rng = np.random.default_rng(seed)
+    ins = np.bincount(rng.integers(0, m, n), minlength=m).astype(np.uint8)
+    assert lb._lib.slos_plan_check(m, n)["children"] == lb.fock_count(m, n)
+    try:
+        lb.set_option("slos_units", 0)
+        a_old, p_old = ctx.slos_amplitudes(U, ins), ctx.slos_basis_probs(U, ins)
+        lb.set_option("slos_units", 1)
+        a_new, p_new = ctx.slos_amplitudes(U, ins), ctx.slos_basis_probs(U, ins)
+    finally:
+        lb.set_option("slos_units", 1)
+    assert np.array_equal(a_new, a_old)
+    assert rel_close(p_new, p_old, 1e-15, 0.0)
+    if lb.fock_count(m, n) <= 50000:
+        assert np.array_equal(ctx.slos_amplitudes(U, ins, order=0), _reorder(lb, m, n, a_new))
+    if lb.fock_count(m, n) <= 20000:
+        keys, amps = O.slos_calculate(U, ins)
+        assert rel_close(a_new, amps, 1e-12, 1e-18)
+
+
+def _reorder(lb, m, n, a_slos):
+    """SLOS-order amplitudes -> fock_basis order through the host rank functions."""
+    S = len(a_slos)  # noqa: N806
+    out = np.zeros(S, dtype=complex)
+    for r in range(S):
+        out[lb.fock_rank(lb.slos_unrank(m, n, r))] = a_slos[r]
+    return out
