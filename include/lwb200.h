@@ -155,6 +155,17 @@ int lwb_sample_dev(lwb_handle h, const double* d_probs, uint64_t S, double thres
                    uint64_t n_samples, uint64_t* d_index, double* d_total);
 int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
                      const double* uniform, uint64_t n_samples, uint64_t* index, double* total);
+/* lwb_basis_sample restricted to the output states SamplerRunner._sample_N_outputs keeps (simulation/sampler.py:275-327):
+ * optional threshold detection (s_i -> min(s_i, 1)), heralded modes holding exactly herald_counts photons, at least
+ * min_detection photons outside the heralded modes, and post-selection rules (sdk/utils/post_selection.py:105-138)
+ * "the photons in modes rule_modes[rule_mode_offsets[q] .. rule_mode_offsets[q+1]) number one of
+ * rule_counts[rule_count_offsets[q] ..)" - modes are FULL-circuit mode indices.  A device kernel zeroes the excluded
+ * states before the CDF is built; *total = probability mass of the kept states. */
+int lwb_basis_sample_selected(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
+                              int threshold_detect, int min_detection, const int32_t* herald_modes,
+                              const int32_t* herald_counts, int n_heralds, const int32_t* rule_modes,
+                              const int32_t* rule_mode_offsets, const int32_t* rule_counts, const int32_t* rule_count_offsets,
+                              int n_rules, const double* uniform, uint64_t n_samples, uint64_t* index, double* total);
 
 /* ---- dense distributions and their merge-convolution -------------------------------------------------
  * pdist_calc / annotated_state_pdist_calc (simulation/probability_distribution.py:25-164): the output distribution

@@ -32,6 +32,7 @@ from .backends import (  # noqa: E402, F401
     PermanentBackend,
     SLOSBackend,
     install,
+    set_array_sampler,
     set_convolve_on_gpu,
     set_n_gpus,
     set_native_source_statistics,

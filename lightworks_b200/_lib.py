@@ -70,6 +70,8 @@ SIGNATURES = {
     "lwb_sample": (_i, [_vp, _vp, _u64, _dbl, _vp, _u64, _vp, _pdbl]),
     "lwb_sample_dev": (_i, [_vp, _vp, _u64, _dbl, _vp, _u64, _vp, _vp]),
     "lwb_basis_sample": (_i, [_vp, _i, _vp, _i, _vp, _dbl, _vp, _u64, _vp, _pdbl]),
+    "lwb_basis_sample_selected": (_i, [_vp, _i, _vp, _i, _vp, _dbl, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _u64,
+                                       _vp, _pdbl]),
     "lwb_keyspace_size": (_i, [_i, _i, _pu64]),
     "lwb_keyspace_index": (_i, [_i, _vp, _pu64]),
     "lwb_keyspace_state": (_i, [_i, _i, _u64, _vp]),
@@ -512,6 +514,29 @@ def _slos_methods():
                                       len(uniform), ptr(idx), C.byref(total)))
         return idx, float(total.value)
 
+    def basis_sample_selected(self, U, in_state, uniform, threshold=1e-9, backend=BACKEND_PERMANENT,  # noqa: N803
+                              threshold_detect=False, min_detection=0, heralds=None, rules=None):
+        """basis_sample restricted to the output states SamplerRunner._sample_N_outputs keeps (sampler.py:275-327):
+        heralds = {mode: photons}, rules = [(modes, allowed photon numbers)] on FULL-circuit modes; the selection is
+        a device mask over the whole basis.  Returns (drawn positions, probability mass of the kept states)."""
+        U, s, _ = _prep(U, in_state)  # noqa: N806
+        uniform = np.ascontiguousarray(uniform, dtype=np.float64)
+        idx = np.zeros(len(uniform), dtype=np.uint64)
+        total = C.c_double(0)
+        heralds = dict(heralds or {})
+        hm = np.array(list(heralds.keys()), dtype=np.int32)
+        hc = np.array(list(heralds.values()), dtype=np.int32)
+        rules = list(rules or [])
+        rm = np.array([m for modes, _ in rules for m in modes], dtype=np.int32)
+        rmo = np.cumsum([0] + [len(modes) for modes, _ in rules]).astype(np.int32)
+        rc = np.array([c for _, counts in rules for c in counts], dtype=np.int32)
+        rco = np.cumsum([0] + [len(counts) for _, counts in rules]).astype(np.int32)
+        check(cdll().lwb_basis_sample_selected(self._h, backend, ptr(U), U.shape[0], ptr(s), float(threshold),
+                                               int(bool(threshold_detect)), int(min_detection), ptr(hm), ptr(hc), len(hm),
+                                               ptr(rm), ptr(rmo), ptr(rc), ptr(rco), len(rules), ptr(uniform),
+                                               len(uniform), ptr(idx), C.byref(total)))
+        return idx, float(total.value)
+
     def dist_zeros(self, n_modes, kmax):
         out = C.c_int(-1)
         check(cdll().lwb_dist_create(self._h, n_modes, kmax, None, C.byref(out)))
@@ -554,7 +579,7 @@ def _slos_methods():
         return DeviceDistribution(self, out.value)
 
     for f in (slos_amplitudes, slos_basis_probs, slos_basis_probs_dev, slos_amplitudes_dev, pdist, sample, sample_dev,
-              basis_sample, dist_zeros, dist_from_dense, dist_from_circuit, dists_from_circuit):
+              basis_sample, basis_sample_selected, dist_zeros, dist_from_dense, dist_from_circuit, dists_from_circuit):
         setattr(Context, f.__name__, f)
 
 

@@ -27,6 +27,7 @@ _state_cls = State
 _settings = None
 _convolve_on_gpu = False
 _native_source = True
+_array_sampler = True  # Sampler tasks run the array-native runner (array_sampler.py); False: the reference's runner
 _n_gpus = 1          # install(n_gpus=N) / set_n_gpus(N): GPUs one process spreads the hot path over
 _comm = None         # the LOCAL communicator shared by every backend object of this process
 
@@ -60,6 +61,14 @@ def set_native_source_statistics(flag: bool) -> None:
     131 s for 8 photons with all three imperfections).  False restores the reference's Python loops."""
     global _native_source
     _native_source = bool(flag)
+
+
+def set_array_sampler(flag: bool) -> None:
+    """After install(), Sampler tasks on a B200 backend run `lightworks_b200.array_sampler` (same distribution, same
+    seeded samples, no `State` object per output state) instead of the reference's SamplerRunner.  On by default;
+    False restores the reference's runner fed by `full_probability_distribution`."""
+    global _array_sampler
+    _array_sampler = bool(flag)
 
 
 def set_convolve_on_gpu(flag: bool) -> None:
@@ -314,6 +323,10 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
     _lib._exc["BackendError"] = LwBackendError
     _lib._exc["PhotonNumberError"] = LwPhotonNumberError
 
+    from . import array_sampler as asmp
+
+    lazy_sim_cls = asmp.make_lazy_simulation_result_class(SimulationResult)
+
     class _BatchedAnalyzerRunner(AnalyzerRunner):
         """AnalyzerRunner with `_get_probs` (simulation/analyzer.py:111-153) evaluated as ONE batched
         device call per photon number instead of one Python call per (input, output) pair."""
@@ -321,6 +334,23 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
         def __init__(self, data, backend):
             super().__init__(data, backend.probability, backend.state_generator)
             self._b = backend
+
+        def run(self):
+            """AnalyzerRunner.run (simulation/analyzer.py:60-108) returning the lazy SimulationResult: the steps and
+            their order are the reference's; only the result object defers building dict[State][State]."""
+            data = self.data
+            inputs = list(data.inputs)
+            check_photon_numbers(inputs, inputs[0].n_photons)
+            pad = [0] * data.circuit.loss_modes
+            full_inputs = [add_heralds_to_state(i, data.circuit.heralds.input) + pad for i in inputs]
+            n_photons = sum(full_inputs[0]) - sum(data.circuit.heralds.output.values())
+            full_outputs, filtered_outputs = self._generate_outputs(data.circuit.input_modes, n_photons)
+            probs = self._get_probs(full_inputs, full_outputs)
+            results = lazy_sim_cls(probs, "probability", inputs=inputs, outputs=filtered_outputs,
+                                   performance=probs.sum() / len(full_inputs))
+            if data.expected is not None:
+                results.error_rate = self._calculate_error_rate(probs, inputs, filtered_outputs, data.expected)
+            return results
 
         def _get_probs(self, full_inputs, full_outputs):
             circuit = self.data.circuit
@@ -366,10 +396,75 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
         full_inputs = [add_heralds_to_state(i, in_heralds) + pad for i in data.inputs]
         amplitudes = np.zeros((len(data.inputs), len(outputs)), dtype=complex)
         amplitudes += self.amplitude_matrix(circuit.U_full, full_inputs, full_outputs)
-        return SimulationResult(amplitudes, "probability_amplitude", inputs=data.inputs, outputs=outputs)
+        return lazy_sim_cls(amplitudes, "probability_amplitude", inputs=data.inputs, outputs=outputs)
 
     def _run_analyzer(self, task):
         return _BatchedAnalyzerRunner(task._generate_task(), self).run()
+
+    from lightworks.emulator.simulation.sampler import SamplerRunner
+    from lightworks.sdk.results import ProbabilityDistribution, SamplingResult
+    from lightworks.sdk.utils.exceptions import SamplerError
+    from lightworks.sdk.utils.post_selection import DefaultPostSelection
+    from lightworks.sdk.utils.random import process_random_seed
+
+    lazy_pd_cls = asmp.make_lazy_distribution_class(ProbabilityDistribution, lw.State)
+
+    def _run_sampler(self, task):
+        """FockBackend.run_sampler (fock_backend.py:67-87) + SamplerRunner (simulation/sampler.py:76-349) on arrays:
+        same cache, same distribution and dict order, same seeded draws, but no State object per output state
+        (lightworks_b200/array_sampler.py).  Annotated inputs (imperfect purity / indistinguishability) go through the
+        device convolution when set_convolve_on_gpu(True), else through the reference's own runner."""
+        data = task._generate_task()
+        circuit = data.circuit
+        runner = SamplerRunner(data, self.full_probability_distribution)  # resolves the default Source / Detector
+        source, detector = runner.source, runner.detector
+        cached = self._check_cache(data)
+        if cached is not None and not isinstance(cached["pdist"], asmp.ArrayDistribution):
+            return FockBackend.run_sampler(self, task)  # cached by the reference runner: let it reuse its dict
+        if cached is not None:
+            dist = cached["pdist"]
+        else:
+            if circuit.input_modes != len(data.input_state):  # sampler.py:82-85
+                raise ValueError("Mismatch in number of modes between input and circuit.")
+            input_state = lw.State(add_heralds_to_state(data.input_state, circuit.heralds.input))
+            all_inputs = source._build_statistics(input_state)
+            if all_inputs and isinstance(next(iter(all_inputs)), AnnotatedState):
+                if not _convolve_on_gpu:
+                    return FockBackend.run_sampler(self, task)
+                from .convolution import pdist_calc as gpu_pdist_calc
+
+                lazy = gpu_pdist_calc(circuit, all_inputs, self)
+                keys, vals = lazy.keys_array, lazy.vals_array
+                if len(vals) == 0:  # sampler.py:99-100
+                    keys, vals = np.zeros((1, circuit.n_modes), dtype=np.uint8), np.ones(1)
+                dist = asmp.ArrayDistribution(np.ascontiguousarray(keys), np.ascontiguousarray(vals), circuit.n_modes)
+            else:
+                dist = asmp.distribution_arrays(self, circuit, all_inputs, _threshold())
+            self._add_to_cache(data, {"pdist": dist, "herald_cache": None})
+        task._probability_distribution = lazy_pd_cls(dist, self)
+        post_selection = DefaultPostSelection() if data.post_selection is None else data.post_selection
+        min_detection = 0 if data.min_detection is None else data.min_detection
+        heralds = circuit.heralds.output
+        if heralds and max(heralds.values()) > 1 and not detector.photon_counting:  # sampler.py:208-216, :285-293
+            raise SamplerError("Non photon number resolving detectors cannot be used when"
+                               "a heralded mode has more than 1 photon.")
+        output_mode = data.sampling_mode != "input"
+        if output_mode and (detector.p_dark > 0 or detector.efficiency < 1):  # sampler.py:276-280
+            raise SamplerError("To use detector dark counts or sub-unity detector efficiency "
+                               "the sampling mode must be set to 'input'.")
+        sel = asmp.Selection(circuit.n_modes, heralds, min_detection, post_selection,
+                             detector.photon_counting if output_mode else True, lw.State)
+        no_states = SamplerError("No output states compatible with provided post-selection/min-detection criteria.")
+        if dist.keys is None:  # the distribution lives on the device
+            counts = asmp.sample_device(self, dist, sel, data.n_samples, data.random_seed, process_random_seed, lw.State,
+                                        detector, "output" if output_mode else "input", no_states)
+        elif output_mode:
+            counts = asmp.sample_n_outputs(dist, sel, data.n_samples, data.random_seed, process_random_seed, lw.State,
+                                           no_states)
+        else:
+            counts, _ = asmp.sample_n_inputs(dist, sel, data.n_samples, data.random_seed, process_random_seed, lw.State,
+                                             detector)
+        return SamplingResult(counts, data.input_state)
 
     def _run(self, task):
         # FockBackend.run is a multimethod object bound to the base implementations
@@ -379,7 +474,9 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
         if isinstance(task, Analyzer) and hasattr(self, "probability_matrix"):
             return _run_analyzer(self, task)
         if isinstance(task, Sampler):
-            return FockBackend.run_sampler(self, task)  # inherits the pdist cache (fock_backend.py:67-87)
+            if _array_sampler:
+                return _run_sampler(self, task)  # array-native runner, shares the pdist cache (fock_backend.py:67-87)
+            return FockBackend.run_sampler(self, task)
         raise LwBackendError("Task not supported on current backend.")
 
     class B200PermanentBackend(PermanentBackendMixin, FockBackend):

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -840,7 +841,15 @@ int lwb::pdist_finish(lwb_handle h, const double* d_probs, int m_tot, int n_mode
         if (first[k] != UINT64_MAX) idx.push_back(k);
     std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return first[a] < first[b]; });
     uint64_t cnt = 0;
-    double total = 0.0;  // sum(pdist.values()) in dict order, permanent.py:159
+    // sum(pdist.values()) in dict order, permanent.py:159.  CPython >= 3.12 adds exact floats with Neumaier
+    // compensation (bltinmodule.c cs_add); the vacuum entry 1 - total below inherits that rounding, so it is restated.
+    double total = 0.0, comp = 0.0;
+    auto py_add = [&](double x) {
+        const double t = total + x;
+        if (std::fabs(total) >= std::fabs(x)) comp += (total - t) + x;
+        else comp += (x - t) + total;
+        total = t;
+    };
     for (uint64_t k : idx) {
         int kk = k_min;
         while (kk < n && k >= key_off[kk + 1]) ++kk;
@@ -850,9 +859,10 @@ int lwb::pdist_finish(lwb_handle h, const double* d_probs, int m_tot, int n_mode
             modes_to_state(x, kk, n_modes, keys + cnt * (uint64_t)n_modes);
             vals[cnt] = marg[k];
         }
-        total += marg[k];
+        py_add(marg[k]);
         ++cnt;
     }
+    total += comp;
     if (backend == LWB_BACKEND_PERMANENT && total < 1.0) {  // permanent.py:160-161 (loss_modes > 0 here)
         if (cnt < cap) {
             memset(keys + cnt * (uint64_t)n_modes, 0, (size_t)n_modes);
@@ -995,11 +1005,10 @@ int lwb_sample(lwb_handle h, const double* probs, uint64_t S, double threshold, 
     return sample_roundtrip(h, (const double*)h->bProbs.p, S, threshold, uniform, n_samples, index, total);
 }
 
-int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
-                     const double* uniform, uint64_t n_samples, uint64_t* index, double* total) {
-    if (!h || !U || !in_state || (n_samples && (!uniform || !index))) return fail(LWB_E_ARG, "null argument");
+// basis distribution of one input on the device (h->bProbs), shared by the sampling entry points
+static int basis_probs_for_sampling(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, int* n_out,
+                                    uint64_t* S_out) {
     if (backend != LWB_BACKEND_PERMANENT && backend != LWB_BACKEND_SLOS) return fail(LWB_E_ARG, "backend %d", backend);
-    std::lock_guard<std::mutex> lk(h->mu);
     int n = 0;
     CK(slos_check(m, in_state, &n));  // size limits shared by both backends
     if (backend == LWB_BACKEND_PERMANENT && n > LWB_K1_MAX_N)
@@ -1020,6 +1029,58 @@ int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const ui
                          (double*)h->bProbs.p));
     } else {
         CK(slos_run_dev(h, (const double*)h->bU.p, m, in_state, 1, 1, (double*)h->bProbs.p));
+    }
+    *n_out = n;
+    *S_out = S;
+    return 0;
+}
+
+int lwb_basis_sample(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
+                     const double* uniform, uint64_t n_samples, uint64_t* index, double* total) {
+    if (!h || !U || !in_state || (n_samples && (!uniform || !index))) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    int n = 0;
+    uint64_t S = 0;
+    CK(basis_probs_for_sampling(h, backend, U, m, in_state, &n, &S));
+    return sample_roundtrip(h, (const double*)h->bProbs.p, S, threshold, uniform, n_samples, index, total);
+}
+
+int lwb_basis_sample_selected(lwb_handle h, int backend, const double* U, int m, const uint8_t* in_state, double threshold,
+                              int threshold_detect, int min_detection, const int32_t* herald_modes,
+                              const int32_t* herald_counts, int n_heralds, const int32_t* rule_modes,
+                              const int32_t* rule_mode_offsets, const int32_t* rule_counts, const int32_t* rule_count_offsets,
+                              int n_rules, const double* uniform, uint64_t n_samples, uint64_t* index, double* total) {
+    if (!h || !U || !in_state || (n_samples && (!uniform || !index))) return fail(LWB_E_ARG, "null argument");
+    if (n_heralds < 0 || n_heralds > 64 || (n_heralds && (!herald_modes || !herald_counts))) return fail(LWB_E_ARG, "heralds");
+    if (n_rules < 0 || n_rules > MASK_MAX_RULES) return fail(LWB_E_LIMIT, "at most %d post-selection rules (got %d)", MASK_MAX_RULES, n_rules);
+    if (n_rules && (!rule_modes || !rule_mode_offsets || !rule_counts || !rule_count_offsets)) return fail(LWB_E_ARG, "rules");
+    std::lock_guard<std::mutex> lk(h->mu);
+    int n = 0;
+    uint64_t S = 0;
+    CK(basis_probs_for_sampling(h, backend, U, m, in_state, &n, &S));
+    if (n > 0) {
+        SelectArgs sa;
+        memset(&sa, 0, sizeof sa);
+        sa.bin = h->d_bin; sa.m = m; sa.n = n; sa.S = S; sa.order = backend == LWB_BACKEND_SLOS ? 1 : 0;
+        sa.threshold_detect = threshold_detect ? 1 : 0; sa.min_detection = min_detection; sa.n_heralds = n_heralds;
+        for (int q = 0; q < n_heralds; ++q) {
+            if (herald_modes[q] < 0 || herald_modes[q] >= m || herald_counts[q] < 0 || herald_counts[q] > 255)
+                return fail(LWB_E_ARG, "herald %d: mode %d count %d", q, herald_modes[q], herald_counts[q]);
+            sa.herald_mode[q] = (uint8_t)herald_modes[q];
+            sa.herald_count[q] = (uint8_t)herald_counts[q];
+        }
+        sa.n_rules = n_rules;
+        for (int q = 0; q < n_rules; ++q) {
+            for (int e = rule_mode_offsets[q]; e < rule_mode_offsets[q + 1]; ++e) {
+                if (rule_modes[e] < 0 || rule_modes[e] >= m) return fail(LWB_E_ARG, "rule %d: mode %d", q, rule_modes[e]);
+                sa.rule_modes[q][rule_modes[e] >> 6] |= 1ull << (rule_modes[e] & 63);
+            }
+            for (int e = rule_count_offsets[q]; e < rule_count_offsets[q + 1]; ++e)
+                if (rule_counts[e] >= 0 && rule_counts[e] < 64) sa.rule_counts[q] |= 1ull << rule_counts[e];
+        }
+        sa.probs = (double*)h->bProbs.p;
+        CK(launch_kmax(h, n, S, 0, sa, select_outputs_kernel<4>, select_outputs_kernel<8>, select_outputs_kernel<12>,
+                       select_outputs_kernel<16>, select_outputs_kernel<24>, select_outputs_kernel<40>));
     }
     return sample_roundtrip(h, (const double*)h->bProbs.p, S, threshold, uniform, n_samples, index, total);
 }

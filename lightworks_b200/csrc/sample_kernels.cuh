@@ -19,7 +19,74 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fock.cuh"
+
 namespace lwb {
+
+// ---------------------------------------------------------------------------------------------------------
+// Output-state selection of SamplerRunner._sample_N_outputs (simulation/sampler.py:275-327) as a device mask over
+// the full basis: a state keeps its probability iff, after optional threshold detection (s_i -> min(s_i, 1),
+// :288-290), every heralded mode holds its required photon number (:292-294), the herald-free state holds at least
+// min_detection photons (:299-300) and every post-selection rule "photons in these modes is one of these numbers"
+// holds (sdk/utils/post_selection.py:105-138; rule modes already mapped to full-circuit modes by the caller).
+// Sampling the masked full-state distribution and then mapping each drawn state (threshold, herald removal) on the
+// host has the same law as the reference's sampling of the merged dict.
+constexpr int MASK_MAX_RULES = 16;
+struct SelectArgs {
+    const uint64_t* bin;
+    int m, n;               // modes, photons
+    uint64_t S;
+    int order;              // 0: fock_basis (colex) ranks, 1: SLOS (lex) ranks
+    int threshold_detect;   // detector without photon counting
+    int min_detection;
+    int n_heralds;
+    uint8_t herald_mode[LWB_MAX_MODES];
+    uint8_t herald_count[LWB_MAX_MODES];
+    int n_rules;
+    unsigned long long rule_modes[MASK_MAX_RULES][2];    // bit j: mode j belongs to the rule (m <= 128)
+    unsigned long long rule_counts[MASK_MAX_RULES];      // bit c: c photons allowed (c < 64)
+    double* probs;          // in place: excluded states are set to 0
+};
+
+template <int KMAX>
+static __global__ void __launch_bounds__(256) select_outputs_kernel(SelectArgs a) {
+    const uint64_t r = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.S) return;
+    int x[KMAX];
+    if (a.order == 0) colex_unrank(a.bin, r, a.n, a.m, x);
+    else lex_unrank(a.bin, r, a.n, a.m, x);
+    // runs of equal modes = (mode, occupation) pairs
+    bool ok = true;
+    int detected = 0;                    // photons seen outside the heralded modes
+    int rule_sum[MASK_MAX_RULES];
+#pragma unroll
+    for (int q = 0; q < MASK_MAX_RULES; ++q) rule_sum[q] = 0;
+    unsigned long long seen_herald = 0;  // heralded modes found occupied (index into the herald list)
+    for (int i = 0; i < a.n;) {
+        int j = i;
+        while (j < a.n && x[j] == x[i]) ++j;
+        const int mode = x[i];
+        const int occ = a.threshold_detect ? 1 : (j - i);
+        int hidx = -1;
+        for (int hq = 0; hq < a.n_heralds; ++hq)
+            if (a.herald_mode[hq] == mode) hidx = hq;
+        if (hidx >= 0) {
+            if (occ != a.herald_count[hidx]) ok = false;
+            seen_herald |= 1ull << (hidx & 63);
+        } else {
+            detected += occ;
+        }
+        for (int q = 0; q < a.n_rules; ++q)
+            if ((a.rule_modes[q][mode >> 6] >> (mode & 63)) & 1ull) rule_sum[q] += occ;
+        i = j;
+    }
+    for (int hq = 0; hq < a.n_heralds; ++hq)  // heralded modes that stayed empty must be required empty
+        if (!((seen_herald >> (hq & 63)) & 1ull) && a.herald_count[hq] != 0) ok = false;
+    if (detected < a.min_detection) ok = false;
+    for (int q = 0; q < a.n_rules; ++q)
+        if (rule_sum[q] > 63 || !((a.rule_counts[q] >> rule_sum[q]) & 1ull)) ok = false;
+    if (!ok) a.probs[r] = 0.0;
+}
 
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 16;

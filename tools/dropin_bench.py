@@ -43,4 +43,15 @@ for name, m, n, seed in [("C1", 6, 3, 1), ("C2", 12, 6, 2), ("m14n7", 14, 7, 7)]
             rows.append({"config": name, "modes": m, "photons": n, "task": task_name, "backend": b,
                          "b200_s": t_gpu, "reference_cpu_s": t_cpu, "speedup": t_cpu / t_gpu})
             print(rows[-1], flush=True)
+# BASELINE config 3 through the unmodified SDK (array-native runner, distribution kept on the device)
+circ = lw.Unitary(lw.random_unitary(24, seed=3))
+st = lw.State([1] * 10 + [0] * 14)
+Backend("permanent").run(lw.Sampler(circ, st, 1000, random_seed=1))
+for b in ("permanent", "slos"):
+    for n_smp in (10_000, 1_000_000):
+        t, res = timeit(lambda: Backend(b).run(lw.Sampler(circ, st, n_smp, random_seed=2)), 2)
+        rows.append({"config": "C3", "modes": 24, "photons": 10, "task": f"Sampler({n_smp} samples)", "backend": b,
+                     "b200_s": t, "reference_cpu_s": None, "distinct_outcomes": len(res),
+                     "note": "reference: ~2 h and > 20 GB of State objects (SURVEY.md 8d), not run"})
+        print(rows[-1], flush=True)
 print(json.dumps(rows))
