@@ -26,7 +26,7 @@ There is no CPU fallback for the numerics: every probability comes from liblwb20
 """
 from __future__ import annotations
 
-from collections import Counter
+from collections.abc import Sequence
 
 import numpy as np
 
@@ -114,6 +114,8 @@ def make_lazy_distribution_class(base, state_cls):
 
         def __eq__(self, other):
             self._fill()
+            if hasattr(other, "_fill"):
+                other._fill()
             return dict.__eq__(self, other)
 
         __hash__ = None
@@ -125,6 +127,108 @@ def make_lazy_distribution_class(base, state_cls):
             return base.__repr__(self)
 
     return LazyProbabilityDistribution
+
+
+class LazyStates(Sequence):
+    """A list of `State` objects over an occupation array uint8[K, m]: objects are created when an element is asked
+    for.  What `SimulationResult.outputs` / `SamplingResult.outputs` hold when a task had thousands of outputs."""
+
+    def __init__(self, rows: np.ndarray, state_cls):
+        self.rows, self._cls, self._cache = rows, state_cls, None
+
+    def _all(self):
+        if self._cache is None:
+            self._cache = [self._cls(r) for r in self.rows.tolist()]
+        return self._cache
+
+    def __len__(self):
+        return len(self.rows)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self._all()[i]
+        if self._cache is not None:
+            return self._cache[i]
+        return self._cls(self.rows[i].tolist())
+
+    def __iter__(self):
+        return iter(self._all())
+
+    def __eq__(self, other):
+        if isinstance(other, LazyStates):
+            return np.array_equal(self.rows, other.rows)
+        return self._all() == other
+
+    __hash__ = None
+
+    def __repr__(self):
+        return repr(self._all())
+
+
+def make_lazy_sampling_result_class(base, state_cls):
+    """A `SamplingResult` (sdk/results/sampling_result.py:33-75) over (rows uint8[K, m], counts[K]): the {State: count}
+    dict - one string hash per distinct outcome - is built when dict access is used."""
+
+    class LazySamplingResult(base):
+        def __init__(self, rows, counts, input):  # noqa: A002
+            if not isinstance(input, state_cls):
+                base.__init__(self, {}, input)  # raises the reference's error
+            dict.__init__(self)
+            self.rows, self.counts, self._ready = rows, counts, False
+            setattr(self, f"_{base.__name__}__input", input)
+            setattr(self, f"_{base.__name__}__outputs", LazyStates(rows, state_cls))
+
+        def _fill(self):
+            if not self._ready:
+                self._ready = True
+                for st, c in zip(self.outputs, self.counts.tolist()):
+                    dict.__setitem__(self, st, int(c))
+
+        def __len__(self):
+            return len(self.counts)
+
+        def __iter__(self):
+            self._fill()
+            return dict.__iter__(self)
+
+        def __contains__(self, k):
+            self._fill()
+            return dict.__contains__(self, k)
+
+        def __getitem__(self, item):
+            self._fill()
+            return base.__getitem__(self, item)
+
+        def keys(self):
+            self._fill()
+            return dict.keys(self)
+
+        def values(self):
+            if not self._ready:
+                return [int(c) for c in self.counts.tolist()]
+            return dict.values(self)
+
+        def items(self):
+            self._fill()
+            return dict.items(self)
+
+        def get(self, k, default=None):
+            self._fill()
+            return dict.get(self, k, default)
+
+        def __eq__(self, other):
+            self._fill()
+            if hasattr(other, "_fill"):
+                other._fill()
+            return dict.__eq__(self, other)
+
+        __hash__ = None
+
+        def __repr__(self):
+            self._fill()
+            return base.__repr__(self)
+
+    return LazySamplingResult
 
 
 def make_lazy_simulation_result_class(base):
@@ -188,6 +292,8 @@ def make_lazy_simulation_result_class(base):
 
         def __eq__(self, other):
             self._fill()
+            if hasattr(other, "_fill"):
+                other._fill()
             return dict.__eq__(self, other)
 
         __hash__ = None
@@ -298,19 +404,23 @@ def _draw(probs: np.ndarray, n_samples: int, seed, normalize: bool, process_seed
 
 
 def _counts_first_seen(samples: np.ndarray):
-    c = Counter(samples.tolist())
-    return np.fromiter(c.keys(), dtype=np.int64, count=len(c)), np.fromiter(c.values(), dtype=np.int64, count=len(c))
+    """Counter(samples): distinct values in first-seen order and their counts."""
+    uniq, first, cnt = np.unique(samples, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    return uniq[order].astype(np.int64), cnt[order].astype(np.int64)
 
 
-def sample_n_outputs(dist: ArrayDistribution, sel: Selection, n_samples: int, seed, process_seed, state_cls, no_states_error):
-    """_sample_N_outputs (:240-327), regime A: returns {State: count} in the reference's order."""
+def sample_n_outputs(dist: ArrayDistribution, sel: Selection, n_samples: int, seed, process_seed, no_states_error):
+    """_sample_N_outputs (:240-327), regime A: (rows, counts) of the drawn states in the reference's order."""
     keys = dist.keys if sel.photon_counting else np.minimum(dist.keys, 1)
     ok = sel.mask(keys)
-    rows, probs = _merge_first_seen(keys[ok][:, sel.kept], dist.vals[ok])
+    rows, probs = keys[ok][:, sel.kept], dist.vals[ok]
+    if sel.heralds or not sel.photon_counting:  # only then can two kept states coincide (:311-314)
+        rows, probs = _merge_first_seen(rows, probs)
     if len(rows) == 0:
         raise no_states_error
     idx, cnt = _counts_first_seen(_draw(probs, n_samples, seed, True, process_seed))
-    return {state_cls(r): int(c) for r, c in zip(rows[idx].tolist(), cnt)}
+    return rows[idx], cnt
 
 
 def sample_n_inputs(dist: ArrayDistribution, sel: Selection, n_samples: int, seed, process_seed, state_cls, detector):
@@ -326,7 +436,8 @@ def sample_n_inputs(dist: ArrayDistribution, sel: Selection, n_samples: int, see
         samples = _draw(dist.vals, n_samples, seed, True, process_seed)
         renorm = dist.vals / total_p
     idx, cnt = _counts_first_seen(samples)
-    return _detect_and_select(dist.keys[idx], cnt, sel, seed, state_cls, detector), renorm
+    rows, counts = _detect_and_select(dist.keys[idx], cnt, sel, seed, state_cls, detector)
+    return rows, counts, renorm
 
 
 def _detect_and_select(states: np.ndarray, counts: np.ndarray, sel: Selection, seed, state_cls, detector):
@@ -340,8 +451,10 @@ def _detect_and_select(states: np.ndarray, counts: np.ndarray, sel: Selection, s
         states = np.array(out, dtype=np.int64).reshape(len(out), states.shape[1])
         counts = np.ones(len(out), dtype=np.int64)
     ok = sel.mask(states)
-    rows, sums = _merge_first_seen(states[ok][:, sel.kept], counts[ok].astype(np.float64))
-    return {state_cls(r): int(c) for r, c in zip(rows.tolist(), sums)}
+    rows, sums = states[ok][:, sel.kept], counts[ok]
+    if sel.heralds or not ideal:  # herald removal / detector noise can map distinct drawn states onto one
+        rows, sums = _merge_first_seen(rows, sums.astype(np.float64))
+    return np.ascontiguousarray(rows, dtype=np.uint8), np.asarray(sums).astype(np.int64)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -375,6 +488,8 @@ def sample_device(backend, dist: ArrayDistribution, sel: Selection, n_samples: i
     if mode == "output":
         if not sel.photon_counting:
             states = np.minimum(states, 1)
-        rows, sums = _merge_first_seen(states[:, sel.kept], cnt.astype(np.float64))
-        return {state_cls(r): int(c) for r, c in zip(rows.tolist(), sums)}
+        rows, sums = states[:, sel.kept], cnt
+        if sel.heralds or not sel.photon_counting:
+            rows, sums = _merge_first_seen(rows, cnt.astype(np.float64))
+        return np.ascontiguousarray(rows, dtype=np.uint8), np.asarray(sums).astype(np.int64)
     return _detect_and_select(states.astype(np.int64), cnt, sel, seed, state_cls, detector)

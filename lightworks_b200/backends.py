@@ -189,6 +189,8 @@ class PermanentBackendMixin(_B200Base):
         return self.ctx.fock_basis(n_modes, n_photons).tolist()
 
     def state_generator_array(self, n_modes: int, n_photons: int) -> np.ndarray:
+        if n_photons == 0:
+            return np.zeros((1, n_modes), dtype=np.uint8)
         return self.ctx.fock_basis(n_modes, n_photons)
 
     def probability_amplitude(self, unitary, input_state, output_state) -> complex:
@@ -199,17 +201,20 @@ class PermanentBackendMixin(_B200Base):
         """permanent.py:85-114: abs(amplitude) ** 2"""
         return abs(self.probability_amplitude(unitary, input_state, output_state)) ** 2
 
+    @staticmethod
+    def _state_array(states) -> np.ndarray:
+        if isinstance(states, np.ndarray):
+            return np.ascontiguousarray(states, dtype=np.uint8)
+        return np.array([_as_list(s) for s in states], dtype=np.uint8)
+
     def amplitude_matrix(self, unitary, inputs, outputs) -> np.ndarray:
-        """All <out|U|in> at once: the double loop of simulation/simulator.py:98-104."""
-        ins = np.array([_as_list(s) for s in inputs], dtype=np.uint8)
-        outs = np.array([_as_list(s) for s in outputs], dtype=np.uint8)
-        return self.ctx.perm_amplitudes(unitary, ins, outs, self._dtype, probs=False)
+        """All <out|U|in> at once: the double loop of simulation/simulator.py:98-104.  States as lists of State /
+        list, or as one uint8 array [K, m]."""
+        return self.ctx.perm_amplitudes(unitary, self._state_array(inputs), self._state_array(outputs), self._dtype, probs=False)
 
     def probability_matrix(self, unitary, inputs, outputs) -> np.ndarray:
         """All |<out|U|in>|^2 at once: the no-loss branch of simulation/analyzer.py:120-125."""
-        ins = np.array([_as_list(s) for s in inputs], dtype=np.uint8)
-        outs = np.array([_as_list(s) for s in outputs], dtype=np.uint8)
-        return self.ctx.perm_amplitudes(unitary, ins, outs, self._dtype, probs=True)
+        return self.ctx.perm_amplitudes(unitary, self._state_array(inputs), self._state_array(outputs), self._dtype, probs=True)
 
     def full_probability_arrays(self, circuit, input_state):
         """(keys, vals) of full_probability_distribution without building Python State objects."""
@@ -313,6 +318,7 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
     from lightworks.sdk.tasks import Analyzer, Sampler, Simulator
     from lightworks.sdk.utils.exceptions import PhotonNumberError as LwPhotonNumberError
     from lightworks.sdk.utils.heralding import add_heralds_to_state
+    from lightworks.sdk.utils.post_selection import DefaultPostSelection
 
     if n_gpus is not None:
         set_n_gpus(n_gpus)
@@ -352,8 +358,31 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
                 results.error_rate = self._calculate_error_rate(probs, inputs, filtered_outputs, data.expected)
             return results
 
+        def _generate_outputs(self, n_modes, n_photons):
+            """analyzer.py:189-225 on arrays when the post-selection is a set of rules (or none): outputs with and
+            without the heralded modes; an arbitrary post-selection function keeps the reference's per-state loop."""
+            data = self.data
+            post = DefaultPostSelection() if data.post_selection is None else data.post_selection
+            rules = getattr(post, "rules", None)
+            if rules is None and type(post).__name__ != "DefaultPostSelection":
+                return super()._generate_outputs(n_modes, n_photons)
+            gen = self._b.state_generator_array
+            if not data.circuit.loss_modes:
+                arr = gen(n_modes, n_photons)
+            else:
+                arr = np.concatenate([gen(n_modes, n) for n in range(n_photons + 1)])
+            ok = np.ones(len(arr), dtype=bool)
+            for r in rules or []:
+                ok &= np.isin(arr[:, list(r.modes)].sum(axis=1), list(r.n_photons))
+            arr = arr[ok]
+            if len(arr) == 0:
+                raise ValueError("No valid outputs found, consider relaxing post-selection.")
+            return _with_heralds(arr, data.circuit.heralds.output, 0), asmp.LazyStates(arr, lw.State)
+
         def _get_probs(self, full_inputs, full_outputs):
             circuit = self.data.circuit
+            if circuit.loss_modes and isinstance(full_outputs, np.ndarray):
+                full_outputs = full_outputs.tolist()
             U, loss = circuit.U_full, circuit.loss_modes  # noqa: N806
             probs = np.zeros((len(full_inputs), len(full_outputs)))
             if not loss:  # analyzer.py:121-125
@@ -377,6 +406,16 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
                         probs[:, j] += p[:, c, q]
             return probs
 
+    def _with_heralds(states: np.ndarray, heralds: dict, pad: int) -> np.ndarray:
+        """add_heralds_to_state (sdk/utils/heralding.py:20-52) + loss-mode padding for an array of states."""
+        k, width = states.shape[0], states.shape[1] + len(heralds)
+        out = np.zeros((k, width + pad), dtype=np.uint8)
+        free = [j for j in range(width) if j not in heralds]
+        out[:, free] = states
+        for mode, count in heralds.items():
+            out[:, mode] = count
+        return out
+
     def _run_simulator(self, task):
         """FockBackend.run_simulator + SimulatorRunner.run (fock_backend.py:53-58, simulator.py:58-111)
         with the inputs x outputs double loop replaced by one batched device call."""
@@ -386,13 +425,15 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
         in_heralds_n, out_heralds_n = sum(in_heralds.values()), sum(out_heralds.values())
         target_n = data.inputs[0].n_photons + in_heralds_n
         check_photon_numbers(data.inputs, target_n - in_heralds_n)
-        if data.outputs is None:
-            outputs = [lw.State(s) for s in self.state_generator(circuit.input_modes, target_n - out_heralds_n)]
+        pad = [0] * circuit.loss_modes
+        if data.outputs is None:  # every output state: stays an array, State objects are made on demand
+            out_arr = self.state_generator_array(circuit.input_modes, target_n - out_heralds_n)
+            outputs = asmp.LazyStates(out_arr, lw.State)
+            full_outputs = _with_heralds(out_arr, out_heralds, circuit.loss_modes)
         else:
             check_photon_numbers(data.outputs, target_n - out_heralds_n)
             outputs = data.outputs
-        pad = [0] * circuit.loss_modes
-        full_outputs = [add_heralds_to_state(o, out_heralds) + pad for o in outputs]
+            full_outputs = [add_heralds_to_state(o, out_heralds) + pad for o in outputs]
         full_inputs = [add_heralds_to_state(i, in_heralds) + pad for i in data.inputs]
         amplitudes = np.zeros((len(data.inputs), len(outputs)), dtype=complex)
         amplitudes += self.amplitude_matrix(circuit.U_full, full_inputs, full_outputs)
@@ -404,10 +445,10 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
     from lightworks.emulator.simulation.sampler import SamplerRunner
     from lightworks.sdk.results import ProbabilityDistribution, SamplingResult
     from lightworks.sdk.utils.exceptions import SamplerError
-    from lightworks.sdk.utils.post_selection import DefaultPostSelection
     from lightworks.sdk.utils.random import process_random_seed
 
     lazy_pd_cls = asmp.make_lazy_distribution_class(ProbabilityDistribution, lw.State)
+    lazy_sr_cls = asmp.make_lazy_sampling_result_class(SamplingResult, lw.State)
 
     def _run_sampler(self, task):
         """FockBackend.run_sampler (fock_backend.py:67-87) + SamplerRunner (simulation/sampler.py:76-349) on arrays:
@@ -456,15 +497,14 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
                              detector.photon_counting if output_mode else True, lw.State)
         no_states = SamplerError("No output states compatible with provided post-selection/min-detection criteria.")
         if dist.keys is None:  # the distribution lives on the device
-            counts = asmp.sample_device(self, dist, sel, data.n_samples, data.random_seed, process_random_seed, lw.State,
-                                        detector, "output" if output_mode else "input", no_states)
+            rows, counts = asmp.sample_device(self, dist, sel, data.n_samples, data.random_seed, process_random_seed,
+                                              lw.State, detector, "output" if output_mode else "input", no_states)
         elif output_mode:
-            counts = asmp.sample_n_outputs(dist, sel, data.n_samples, data.random_seed, process_random_seed, lw.State,
-                                           no_states)
+            rows, counts = asmp.sample_n_outputs(dist, sel, data.n_samples, data.random_seed, process_random_seed, no_states)
         else:
-            counts, _ = asmp.sample_n_inputs(dist, sel, data.n_samples, data.random_seed, process_random_seed, lw.State,
-                                             detector)
-        return SamplingResult(counts, data.input_state)
+            rows, counts, _ = asmp.sample_n_inputs(dist, sel, data.n_samples, data.random_seed, process_random_seed,
+                                                   lw.State, detector)
+        return lazy_sr_cls(rows, counts, data.input_state)
 
     def _run(self, task):
         # FockBackend.run is a multimethod object bound to the base implementations

@@ -79,6 +79,43 @@ __device__ __forceinline__ double2 su_cmul_py(double2 a, double2 b) {  // CPytho
     return r;
 }
 
+constexpr int SU_R = 4;  // children per thread and pass (strided by the block size: every access stays coalesced)
+
+// Trailing part of one child, D trailing photons (compile-time: exact unrolling, constant shifts).  Terms in ascending
+// mode order; the run of mode l, if the prefix holds l, was merged into the last prefix term by the caller.
+template <int D>
+__device__ __forceinline__ void su_trailing(uint64_t y, uint32_t c, int ell, bool has_ell, const uint32_t* __restrict__ ht,
+                                            int mv, const double2* __restrict__ pb, const double2* __restrict__ ucol,
+                                            const double* __restrict__ sq, double2& acc) {
+    const uint32_t lo = (uint32_t)y, hi = (uint32_t)(y >> 32);
+    uint32_t Q = 0;
+    int prev = ell, run = 0;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+        const int yi = (int)(((i < 4 ? lo : hi) >> (8 * (i & 3))) & 0xffu);
+        const int r = D - 1 - i;
+        Q += ht[r * mv + prev] - ht[r * mv + yi];
+        run += 1;
+        bool last_of_run = true;
+        if (i + 1 < D) last_of_run = (int)((((i + 1) < 4 ? lo : hi) >> (8 * ((i + 1) & 3))) & 0xffu) != yi;
+        if (last_of_run) {
+            if (!(has_ell && yi == ell)) {
+                double2 t = pb[c - Q];
+                if (run > 1) {
+                    const double f = sq[run];
+                    t.x = __dmul_rn(f, t.x);
+                    t.y = __dmul_rn(f, t.y);
+                }
+                const double2 term = su_cmul_py(t, ucol[yi]);
+                acc.x = __dadd_rn(acc.x, term.x);
+                acc.y = __dadd_rn(acc.y, term.y);
+            }
+            run = 0;
+        }
+        prev = yi;
+    }
+}
+
 __global__ void __launch_bounds__(SU_THREADS) slos_units_kernel(SlosUnitsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.m, mv = m + 1;
@@ -104,64 +141,66 @@ __global__ void __launch_bounds__(SU_THREADS) slos_units_kernel(SlosUnitsArgs a)
         const int d = un.d, np = un.np, ell = un.ell;
         const bool has_ell = un.has_ell != 0;
         const uint64_t* lut = a.lut + un.lut;
-        for (uint32_t c = tid; c < T; c += SU_THREADS) {
-            const uint64_t y = lut[c];
-            // photons of the trailing part that sit in mode l (they extend the prefix's run of l)
-            int lead = 0;
-            if (has_ell) {
+        const uint32_t ell4 = (uint32_t)ell * 0x01010101u;
+        for (uint32_t base = 0; base < T; base += SU_THREADS * SU_R) {
+            // SU_R children per thread, strided by the block size: child j of this thread is c0 + j * SU_THREADS
+            const uint32_t c0 = base + tid;
+            uint64_t y[SU_R];
+            double2 acc[SU_R];
+            int lead[SU_R];
 #pragma unroll
-                for (int i = 0; i < SU_DMAX; ++i)
-                    if (i < d && (int)((y >> (8 * i)) & 0xff) == ell && lead == i) lead = i + 1;
+            for (int j = 0; j < SU_R; ++j) {
+                const uint32_t c = c0 + j * SU_THREADS;
+                y[j] = c < T ? lut[c] : ~0ull;
+                acc[j] = make_double2(0.0, 0.0);
+                // trailing photons sitting in mode l extend the prefix's run of l (unused bytes of y are 0xff)
+                lead[j] = has_ell ? (__popc(__vcmpeq4((uint32_t)y[j], ell4)) + __popc(__vcmpeq4((uint32_t)(y[j] >> 32), ell4))) >> 3 : 0;
             }
-            double2 acc = make_double2(0.0, 0.0);
-            // ---- prefix modes, ascending: one end-aligned coalesced stream each ----
+            // ---- prefix modes, ascending: one end-aligned coalesced stream each; constants hoisted per stream ----
             for (int s = 0; s < np; ++s) {
-                double2 t = a.parent[un.sbase[s] + c];
-                int mult = un.pmult[s];
-                if (s == np - 1) mult += lead;  // only the last prefix mode can equal l
-                if (mult > 1) {
-                    const double f = sq[mult];
-                    t.x = __dmul_rn(f, t.x);
-                    t.y = __dmul_rn(f, t.y);
+                const double2 uv = ucol[un.pm[s]];
+                const int pmul = un.pmult[s];
+                const bool last_stream = s == np - 1;  // the only prefix mode that can equal l
+                const double2* __restrict__ sp = a.parent + un.sbase[s] + c0;
+#pragma unroll
+                for (int j = 0; j < SU_R; ++j) {
+                    if (c0 + j * SU_THREADS < T) {
+                        double2 t = sp[j * SU_THREADS];
+                        const int mult = pmul + (last_stream ? lead[j] : 0);
+                        if (mult > 1) {
+                            const double f = sq[mult];
+                            t.x = __dmul_rn(f, t.x);
+                            t.y = __dmul_rn(f, t.y);
+                        }
+                        const double2 term = su_cmul_py(t, uv);
+                        acc[j].x = __dadd_rn(acc[j].x, term.x);
+                        acc[j].y = __dadd_rn(acc[j].y, term.y);
+                    }
                 }
-                const double2 term = su_cmul_py(t, ucol[un.pm[s]]);
-                acc.x = __dadd_rn(acc.x, term.x);
-                acc.y = __dadd_rn(acc.y, term.y);
             }
             // ---- trailing modes, ascending: parents inside the staged block B(P) ----
-            uint32_t Q = 0;
-            int prev = ell, run = 0;
 #pragma unroll
-            for (int i = 0; i < SU_DMAX; ++i) {
-                if (i < d) {
-                    const int yi = (int)((y >> (8 * i)) & 0xff);
-                    const int r = d - 1 - i;
-                    Q += ht[r * mv + prev] - ht[r * mv + yi];
-                    run += 1;
-                    const int ynext = (i + 1 < SU_DMAX) ? (int)((y >> (8 * ((i + 1) & 7))) & 0xff) : 0;
-                    const bool last_of_run = (i == d - 1) || (ynext != yi);
-                    if (last_of_run) {
-                        if (!(has_ell && yi == ell)) {  // the run of l was merged into the last prefix term
-                            double2 t = pb[c - Q];
-                            if (run > 1) {
-                                const double f = sq[run];
-                                t.x = __dmul_rn(f, t.x);
-                                t.y = __dmul_rn(f, t.y);
-                            }
-                            const double2 term = su_cmul_py(t, ucol[yi]);
-                            acc.x = __dadd_rn(acc.x, term.x);
-                            acc.y = __dadd_rn(acc.y, term.y);
-                        }
-                        run = 0;
+            for (int j = 0; j < SU_R; ++j) {
+                const uint32_t c = c0 + j * SU_THREADS;
+                if (c < T) {
+                    switch (d) {  // block-uniform
+                        case 1: su_trailing<1>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        case 2: su_trailing<2>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        case 3: su_trailing<3>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        case 4: su_trailing<4>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        case 5: su_trailing<5>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        case 6: su_trailing<6>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        case 7: su_trailing<7>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
+                        default: su_trailing<8>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
                     }
-                    prev = yi;
+                    const uint64_t rank = un.start + c;
+                    if (a.write_probs)  // abs(a) ** 2 (slos.py:74); x*x + y*y differs from hypot(x, y)^2 by <= 2 ulp
+                        reinterpret_cast<double*>(a.child)[rank] =
+                            __dadd_rn(__dmul_rn(acc[j].x, acc[j].x), __dmul_rn(acc[j].y, acc[j].y));
+                    else
+                        reinterpret_cast<double2*>(a.child)[rank] = acc[j];
                 }
             }
-            const uint64_t rank = un.start + c;
-            if (a.write_probs)  // abs(a) ** 2 (slos.py:74); x*x + y*y differs from hypot(x, y)^2 by <= 2 ulp
-                reinterpret_cast<double*>(a.child)[rank] = __dadd_rn(__dmul_rn(acc.x, acc.x), __dmul_rn(acc.y, acc.y));
-            else
-                reinterpret_cast<double2*>(a.child)[rank] = acc;
         }
     }
 }
@@ -280,8 +319,8 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
         const int lo = m - b.nf_max[d];
         for (int i = 0; i < d; ++i) y[i] = lo;
         for (uint64_t c = 0; c < lut_size[d]; ++c) {
-            uint64_t w = 0;
-            for (int i = 0; i < d; ++i) w |= (uint64_t)y[i] << (8 * i);
+            uint64_t w = ~0ull;  // unused bytes stay 0xff (never equal to a mode)
+            for (int i = 0; i < d; ++i) w = (w & ~(0xffull << (8 * i))) | ((uint64_t)y[i] << (8 * i));
             lut.push_back(w);
             for (int i = d - 1; i >= 0; --i)  // lex successor
                 if (y[i] < m - 1) {

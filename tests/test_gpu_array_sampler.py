@@ -87,7 +87,7 @@ def test_device_regime_matches_host_regime_statistically(lb, monkeypatch):
         ps = PostSelection()
         ps.add((0, 1), (0, 1))
         for mode, det in (("output", Detector(photon_counting=False)), ("input", Detector())):
-            mk = lambda seed: lw.Sampler(circ, lw.State([1, 0, 1, 1, 0, 1, 0, 0, 0]), 200_000, random_seed=seed,  # noqa: E731
+            mk = lambda seed: lw.Sampler(circ, lw.State([1, 0, 1, 1, 0, 1, 0, 0]), 200_000, random_seed=seed,  # noqa: E731
                                          post_selection=ps, min_detection=2, detector=det, sampling_mode=mode)
             exact = Backend("permanent").run(mk(1))
             monkeypatch.setattr(asmp, "REGIME_A_MAX", 100)
