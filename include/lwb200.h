@@ -82,6 +82,8 @@ int lwb_fock_unrank(int m, int n, uint64_t rank, uint8_t* state);
 /* SLOS (dict insertion) order of slos.py:96-103 */
 int lwb_slos_rank(int m, const uint8_t* state, uint64_t* rank);
 int lwb_slos_unrank(int m, int n, uint64_t rank, uint8_t* state);
+/* Occupation vectors of `count` states given by their positions in the SLOS order (host). */
+int lwb_slos_states(int m, int n, const uint64_t* ranks, uint64_t count, uint8_t* states);
 /* States [r0, r0+cnt) of fock_basis(m, n) enumerated on the device; states: cnt*m bytes. */
 int lwb_fock_basis(lwb_handle h, int m, int n, uint64_t r0, uint64_t cnt, uint8_t* states);
 int lwb_fock_basis_dev(lwb_handle h, int m, int n, uint64_t r0, uint64_t cnt, uint8_t* d_states);
@@ -100,6 +102,13 @@ int lwb_perm_amplitudes(lwb_handle h, const double* U, int m, const uint8_t* ins
 int lwb_perm_amplitudes_dev(lwb_handle h, const double* d_U, int m, const uint8_t* d_ins, int n_in,
                             const uint8_t* d_outs, uint64_t n_out, int n_photons, int dtype,
                             int want_probs, double* d_out);
+
+/* Batch across unitaries: lightworks.Batch (sdk/tasks/batch.py:45-58) holds tasks that typically differ only in the
+ * circuit parameters; the reference runs them one by one (emulator/backends/backend.py:102-103).  n_tasks unitaries
+ * U[n_tasks][m][m], inputs ins[n_tasks][n_in][m] (or one shared set [n_in][m] when shared_inputs != 0), shared outputs
+ * outs[n_out][m], all with the same photon number; out[n_tasks][n_in][n_out] (complex or |amp|^2).  One launch. */
+int lwb_perm_amplitudes_batch(lwb_handle h, const double* U, int n_tasks, int m, const uint8_t* ins, int n_in,
+                              int shared_inputs, const uint8_t* outs, uint64_t n_out, int dtype, int want_probs, double* out);
 
 /* The loop body of PermanentBackend.full_probability_distribution (permanent.py:145-150) over the
  * rank range [r0, r0+cnt) of fock_basis(m, n): probs[k] = |<basis[r0+k]|U|in>|^2.  Output states

@@ -57,6 +57,7 @@ SIGNATURES = {
     "lwb_perm_matrices": (_i, [_vp, _vp, _u64, _i, _i, _vp]),
     "lwb_perm_matrices_dev": (_i, [_vp, _vp, _u64, _i, _i, _vp]),
     "lwb_perm_amplitudes": (_i, [_vp, _vp, _i, _vp, _i, _vp, _u64, _i, _i, _vp]),
+    "lwb_perm_amplitudes_batch": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _u64, _i, _i, _vp]),
     "lwb_perm_amplitudes_dev": (_i, [_vp, _vp, _i, _vp, _i, _vp, _u64, _i, _i, _i, _vp]),
     "lwb_perm_basis_probs": (_i, [_vp, _vp, _i, _vp, _u64, _u64, _i, _vp]),
     "lwb_perm_basis_probs_dev": (_i, [_vp, _vp, _i, _vp, _i, _u64, _u64, _i, _vp]),
@@ -76,6 +77,7 @@ SIGNATURES = {
     "lwb_keyspace_index": (_i, [_i, _vp, _pu64]),
     "lwb_keyspace_state": (_i, [_i, _i, _u64, _vp]),
     "lwb_keyspace_states": (_i, [_i, _i, _vp, _u64, _vp]),
+    "lwb_slos_states": (_i, [_i, _i, _vp, _u64, _vp]),
     "lwb_dist_create": (_i, [_vp, _i, _i, _vp, _pi]),
     "lwb_dist_from_circuit": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _i, _pi]),
     "lwb_dist_convolve": (_i, [_vp, _i, _i, _pi]),
@@ -221,6 +223,14 @@ def keyspace_states(n_modes: int, kmax: int, indices) -> np.ndarray:
     idx = np.ascontiguousarray(indices, dtype=np.uint64)
     out = np.zeros((len(idx), n_modes), dtype=np.uint8)
     check(cdll().lwb_keyspace_states(n_modes, kmax, ptr(idx), len(idx), ptr(out)))
+    return out
+
+
+def slos_states(m: int, n: int, ranks) -> np.ndarray:
+    """Occupation vectors of the states at the given positions of the SLOS (dict insertion) order of (m, n)."""
+    idx = np.ascontiguousarray(ranks, dtype=np.uint64)
+    out = np.zeros((len(idx), m), dtype=np.uint8)
+    check(cdll().lwb_slos_states(m, n, ptr(idx), len(idx), ptr(out)))
     return out
 
 
@@ -407,6 +417,24 @@ class Context:
         out = np.zeros((ins.shape[0], outs.shape[0]), dtype=np.float64 if probs else np.complex128)
         check(cdll().lwb_perm_amplitudes(self._h, ptr(U), m, ptr(ins), ins.shape[0], ptr(outs), outs.shape[0],
                                          dtype, int(probs), ptr(out)))
+        return out
+
+    def perm_amplitudes_batch(self, U, ins, outs, dtype: int = LWB_C128, probs: bool = False) -> np.ndarray:  # noqa: N803
+        """lwb_perm_amplitudes_batch: U [B, m, m], ins [B, n_in, m] (or [n_in, m] shared by every task), outs [n_out, m]
+        -> [B, n_in, n_out] amplitudes (or probabilities), one launch for the whole batch."""
+        U = np.ascontiguousarray(U, dtype=np.complex128)  # noqa: N806
+        ins = np.ascontiguousarray(ins, dtype=np.uint8)
+        outs = np.ascontiguousarray(np.atleast_2d(outs), dtype=np.uint8)
+        if U.ndim != 3 or U.shape[1] != U.shape[2]:
+            raise ValueError("expected unitaries of shape (B, m, m)")
+        b, m = U.shape[0], U.shape[1]
+        shared = ins.ndim == 2
+        if ins.shape[-1] != m or outs.shape[1] != m or (not shared and (ins.ndim != 3 or ins.shape[0] != b)):
+            raise ValueError("unitary / state dimensions do not match")
+        n_in = ins.shape[-2]
+        out = np.zeros((b, n_in, outs.shape[0]), dtype=np.float64 if probs else np.complex128)
+        check(cdll().lwb_perm_amplitudes_batch(self._h, ptr(U), b, m, ptr(ins), n_in, int(shared), ptr(outs), outs.shape[0],
+                                               dtype, int(probs), ptr(out)))
         return out
 
     def perm_basis_probs(self, U, in_state, r0: int = 0, cnt: int | None = None, dtype: int = LWB_C128,  # noqa: N803

@@ -68,7 +68,7 @@ def make_lazy_distribution_class(base, state_cls):
                 if backend_id == _lib.BACKEND_PERMANENT:
                     keys = _lib.keyspace_states(d.n_modes, int(sum(ins)), idx + off)
                 else:
-                    keys = np.array([_lib.slos_unrank(d.n_modes, int(sum(ins)), int(r)) for r in idx], dtype=np.uint8)
+                    keys = _lib.slos_states(d.n_modes, int(sum(ins)), idx)
                 d.keys, d.vals = keys, p[idx]
             return d.keys, d.vals
 
@@ -117,6 +117,10 @@ def make_lazy_distribution_class(base, state_cls):
             if hasattr(other, "_fill"):
                 other._fill()
             return dict.__eq__(self, other)
+
+        def __ne__(self, other):  # dict defines its own __ne__: without this, != would compare the unfilled dicts
+            eq = self.__eq__(other)
+            return eq if eq is NotImplemented else not eq
 
         __hash__ = None
 
@@ -222,6 +226,10 @@ def make_lazy_sampling_result_class(base, state_cls):
                 other._fill()
             return dict.__eq__(self, other)
 
+        def __ne__(self, other):  # dict defines its own __ne__: without this, != would compare the unfilled dicts
+            eq = self.__eq__(other)
+            return eq if eq is NotImplemented else not eq
+
         __hash__ = None
 
         def __repr__(self):
@@ -295,6 +303,10 @@ def make_lazy_simulation_result_class(base):
             if hasattr(other, "_fill"):
                 other._fill()
             return dict.__eq__(self, other)
+
+        def __ne__(self, other):  # dict defines its own __ne__: without this, != would compare the unfilled dicts
+            eq = self.__eq__(other)
+            return eq if eq is NotImplemented else not eq
 
         __hash__ = None
 
@@ -484,7 +496,7 @@ def sample_device(backend, dist: ArrayDistribution, sel: Selection, n_samples: i
         off = _lib.keyspace_size(m, n - 1) if n else 0
         states = _lib.keyspace_states(m, n, uidx.astype(np.uint64) + off)
     else:
-        states = np.array([_lib.slos_unrank(m, n, int(r)) for r in uidx], dtype=np.uint8).reshape(len(uidx), m)
+        states = _lib.slos_states(m, n, uidx)
     if mode == "output":
         if not sel.photon_counting:
             states = np.minimum(states, 1)

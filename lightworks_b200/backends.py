@@ -416,10 +416,8 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
             out[:, mode] = count
         return out
 
-    def _run_simulator(self, task):
-        """FockBackend.run_simulator + SimulatorRunner.run (fock_backend.py:53-58, simulator.py:58-111)
-        with the inputs x outputs double loop replaced by one batched device call."""
-        data = task._generate_task()
+    def _prepare_simulator(self, data):
+        """The state bookkeeping of SimulatorRunner.run (simulator.py:70-100): (outputs, full inputs, full outputs)."""
         circuit = data.circuit
         in_heralds, out_heralds = circuit.heralds.input, circuit.heralds.output
         in_heralds_n, out_heralds_n = sum(in_heralds.values()), sum(out_heralds.values())
@@ -433,11 +431,41 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
         else:
             check_photon_numbers(data.outputs, target_n - out_heralds_n)
             outputs = data.outputs
-            full_outputs = [add_heralds_to_state(o, out_heralds) + pad for o in outputs]
-        full_inputs = [add_heralds_to_state(i, in_heralds) + pad for i in data.inputs]
+            full_outputs = np.array([add_heralds_to_state(o, out_heralds) + pad for o in outputs], dtype=np.uint8)
+        full_inputs = np.array([add_heralds_to_state(i, in_heralds) + pad for i in data.inputs], dtype=np.uint8)
+        return outputs, full_inputs, full_outputs
+
+    def _run_simulator(self, task):
+        """FockBackend.run_simulator + SimulatorRunner.run (fock_backend.py:53-58, simulator.py:58-111)
+        with the inputs x outputs double loop replaced by one batched device call."""
+        data = task._generate_task()
+        outputs, full_inputs, full_outputs = _prepare_simulator(self, data)
         amplitudes = np.zeros((len(data.inputs), len(outputs)), dtype=complex)
-        amplitudes += self.amplitude_matrix(circuit.U_full, full_inputs, full_outputs)
+        amplitudes += self.amplitude_matrix(data.circuit.U_full, full_inputs, full_outputs)
         return lazy_sim_cls(amplitudes, "probability_amplitude", inputs=data.inputs, outputs=outputs)
+
+    def _run_simulator_batch(self, tasks):
+        """lightworks.Batch of Simulator tasks (sdk/tasks/batch.py:45-58; run one by one at backends/backend.py:102-103):
+        tasks whose circuits have the same size and whose full-width outputs coincide - a parameter scan, the
+        tomography circuits - go to the device as ONE launch with a table of unitaries (lwb_perm_amplitudes_batch);
+        anything else falls back to task-by-task.  Results in task order."""
+        prepared = []
+        for t in tasks:
+            data = t._generate_task()
+            prepared.append((data, *_prepare_simulator(self, data)))
+        results = [None] * len(tasks)
+        groups: dict[tuple, list[int]] = {}
+        for i, (data, _outs, fin, fout) in enumerate(prepared):
+            groups.setdefault((data.circuit.U_full.shape, fin.shape, fout.shape, fout.tobytes()), []).append(i)
+        for idxs in groups.values():
+            first = prepared[idxs[0]]
+            U = np.stack([prepared[i][0].circuit.U_full for i in idxs])  # noqa: N806
+            ins = np.stack([prepared[i][2] for i in idxs])
+            amps = self.ctx.perm_amplitudes_batch(U, ins, first[3], self._dtype, probs=False)
+            for k, i in enumerate(idxs):
+                data, outs = prepared[i][0], prepared[i][1]
+                results[i] = lazy_sim_cls(amps[k] + 0, "probability_amplitude", inputs=data.inputs, outputs=outs)
+        return results
 
     def _run_analyzer(self, task):
         return _BatchedAnalyzerRunner(task._generate_task(), self).run()
@@ -524,6 +552,22 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
             PermanentBackendMixin.__init__(self, device, dtype)
 
         run = _run
+        run_simulator_batch = _run_simulator_batch
+
+    from lightworks.sdk.tasks import Batch
+
+    ref_run_batch = LwBackend._run_batch
+
+    def _run_batch(self, task: Batch):
+        """Backend._run_batch (backends/backend.py:101-103): a Batch made only of Simulator tasks on the B200
+        permanent backend runs as one device launch; everything else keeps the reference's task-by-task loop."""
+        tasks = list(task)
+        be = self._backend
+        if tasks and isinstance(be, B200PermanentBackend) and all(type(t) is Simulator for t in tasks):
+            return be.run_simulator_batch(tasks)
+        return [self._run(t) for t in tasks]
+
+    LwBackend._run.register(_run_batch)
 
     class B200SLOSBackend(SLOSBackendMixin, FockBackend):
         def __init__(self):
@@ -567,7 +611,7 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
     _installed = {"old_map": LwBackend._backend_map, "classes": (B200PermanentBackend, B200SLOSBackend),
                   "Backend": LwBackend, "pkg": lw_backends_pkg, "patched": patch_names,
                   "ref": (RefPermanent, RefSLOS), "sampler_mod": lw_sampler_mod, "ref_pdist_calc": ref_pdist_calc,
-                  "source_cls": LwSource, "ref_build_statistics": ref_build_statistics}
+                  "source_cls": LwSource, "ref_build_statistics": ref_build_statistics, "ref_run_batch": ref_run_batch}
     if patch_names:
         lw_backends_pkg.PermanentBackend = B200PermanentBackend
         lw_backends_pkg.SLOSBackend = B200SLOSBackend
@@ -590,6 +634,7 @@ def uninstall():
         _installed["pkg"].PermanentBackend, _installed["pkg"].SLOSBackend = _installed["ref"]
     _installed["sampler_mod"].pdist_calc = _installed["ref_pdist_calc"]
     _installed["source_cls"]._build_statistics = _installed["ref_build_statistics"]
+    _installed["Backend"]._run.register(_installed["ref_run_batch"])
     _installed = None
     _state_cls = State
     _settings = None

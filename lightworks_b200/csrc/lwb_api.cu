@@ -404,9 +404,18 @@ int lwb::launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* d_
     uint64_t need = (n_out + gpb - 1) / gpb;
     uint64_t gx = std::max<uint64_t>(1, (uint64_t)resident / (uint64_t)n_in);
     gx = std::min<uint64_t>(need, gx);
-    PermStatesArgs a{(const double2*)d_U, m, d_ins, d_outs, r0, n_out, h->d_bin, d_out, want_probs, h->mirror};
+    PermStatesArgs a{(const double2*)d_U, m, d_ins, d_outs, r0, n_out, h->d_bin, d_out, want_probs, h->mirror, 0, 0, 0};
     if (!want_probs) a.mir.n = 0;
-    dim3 grid((unsigned)gx, (unsigned)n_in, 1);
+    unsigned gz = 1;
+    if (h->batch_tasks > 1) {  // lwb_perm_amplitudes_batch: one launch for every unitary of the batch
+        gz = (unsigned)h->batch_tasks;
+        a.u_stride = (uint64_t)m * m;
+        a.in_stride = h->batch_shared_inputs ? 0 : (uint64_t)n_in * m;
+        a.out_stride = (uint64_t)n_in * n_out * (want_probs ? 1 : 2);
+        a.mir.n = 0;
+        gx = std::max<uint64_t>(1, gx / gz);
+    }
+    dim3 grid((unsigned)gx, (unsigned)n_in, gz);
     fn<<<grid, K1_THREADS, smem, h->stream>>>(a);
     h->launches++;
     CU(cudaGetLastError());
@@ -455,6 +464,52 @@ int lwb_perm_amplitudes(lwb_handle h, const double* U, int m, const uint8_t* ins
     CK(launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, n_in, (const uint8_t*)h->bOut.p, 0,
                      n_out, n, dtype, want_probs, (double*)h->bRes.p));
     CU(cudaMemcpyAsync(out, h->bRes.p, (size_t)n_in * n_out * per, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// Batch across unitaries (sdk/tasks/batch.py:45-58, run serially by emulator/backends/backend.py:102-103): B tasks that
+// differ in U (and optionally in their inputs) but share photon number and output states, ONE kernel launch.
+int lwb_perm_amplitudes_batch(lwb_handle h, const double* U, int n_tasks, int m, const uint8_t* ins, int n_in,
+                              int shared_inputs, const uint8_t* outs, uint64_t n_out, int dtype, int want_probs, double* out) {
+    if (!h || !U || !ins || !outs || !out) return fail(LWB_E_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
+    if (n_tasks < 1 || n_tasks > 65535) return fail(LWB_E_ARG, "n_tasks=%d outside [1,65535]", n_tasks);
+    if (n_in < 1) return fail(LWB_E_ARG, "n_in=%d", n_in);
+    if (n_out == 0) return 0;
+    const int n = photons_of(ins, m);
+    const size_t n_in_rows = (size_t)(shared_inputs ? 1 : n_tasks) * n_in;
+    for (size_t i = 0; i < n_in_rows; ++i)
+        if (photons_of(ins + i * m, m) != n) return fail(LWB_E_PHOTONS, "input %zu holds a different photon number", i);
+    for (uint64_t j = 0; j < n_out; ++j)
+        if (photons_of(outs + j * m, m) != n)
+            return fail(LWB_E_PHOTONS, "output %llu holds %d photons, inputs hold %d", (unsigned long long)j,
+                        photons_of(outs + j * m, m), n);
+    const size_t per = want_probs ? 8 : 16;
+    const size_t total = (size_t)n_tasks * n_in * n_out;
+    if (n == 0) {
+        for (size_t k = 0; k < total; ++k) {
+            if (want_probs) out[k] = 1.0;
+            else { out[2 * k] = 1.0; out[2 * k + 1] = 0.0; }
+        }
+        return 0;
+    }
+    CU(cudaSetDevice(h->device));
+    CK(ensure(h, h->bU, (size_t)n_tasks * m * m * 16));
+    CK(ensure(h, h->bIn, n_in_rows * m));
+    CK(ensure(h, h->bOut, n_out * (uint64_t)m));
+    CK(ensure(h, h->bRes, total * per));
+    CU(cudaMemcpyAsync(h->bU.p, U, (size_t)n_tasks * m * m * 16, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->bIn.p, ins, n_in_rows * m, cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->bOut.p, outs, n_out * (uint64_t)m, cudaMemcpyHostToDevice, h->stream));
+    h->batch_tasks = n_tasks;
+    h->batch_shared_inputs = shared_inputs ? 1 : 0;
+    const int rc = launch_states(h, (const double*)h->bU.p, m, (const uint8_t*)h->bIn.p, n_in, (const uint8_t*)h->bOut.p, 0,
+                                 n_out, n, dtype, want_probs, (double*)h->bRes.p);
+    h->batch_tasks = 0;
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(out, h->bRes.p, total * per, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return 0;
 }
@@ -1238,6 +1293,19 @@ int lwb_keyspace_states(int n_modes, int kmax, const uint64_t* indices, uint64_t
         int x[LWB_MAX_PHOTONS + 1];
         colex_unrank(host_bin(), index - off[k], k, n_modes, x);
         modes_to_state(x, k, n_modes, states + c * (uint64_t)n_modes);
+    }
+    return 0;
+}
+
+int lwb_slos_states(int m, int n, const uint64_t* ranks, uint64_t count, uint8_t* states) {
+    if (count && (!ranks || !states)) return fail(LWB_E_ARG, "null argument");
+    CK(check_mn(m, n));
+    const uint64_t S = binom(host_bin(), m + n - 1, n);
+    for (uint64_t c = 0; c < count; ++c) {
+        if (ranks[c] >= S) return fail(LWB_E_ARG, "rank out of range");
+        int x[LWB_MAX_PHOTONS + 1];
+        lex_unrank(host_bin(), ranks[c], n, m, x);
+        modes_to_state(x, n, m, states + c * (uint64_t)m);
     }
     return 0;
 }

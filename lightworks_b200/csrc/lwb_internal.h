@@ -49,6 +49,7 @@ struct lwb_context {
     uint64_t launches = 0;
     lwb::K1xState* k1x = nullptr;
     lwb::SlosUnitsState* slos_units = nullptr;  // cached K3u plans per (m, k)
+    int batch_tasks = 0, batch_shared_inputs = 0;  // set around lwb_perm_amplitudes_batch's launch (blockIdx.z = task)
     lwb::MirrorSet mirror = {};  // set by the communicator around a sharded launch: peers receiving every probability
     struct DistSlot {  // dense distribution over the key space K(n_modes, kmax), device resident
         double* p = nullptr;

@@ -71,6 +71,9 @@ struct PermStatesArgs {
     double* out;               // [n_in][n_out] complex (2 doubles) or real
     int out_probs;             // 0: amplitudes, 1: |amp|^2
     MirrorSet mir;             // out_probs only: peers that receive every probability as it is produced
+    // Batch across unitaries (blockIdx.z = task): task z uses U + z * u_stride (complex entries), inputs
+    // in_states + z * in_stride (bytes) and writes out + z * out_stride (doubles); outputs are shared.  0 = no batch.
+    uint64_t u_stride, in_stride, out_stride;
 };
 
 template <typename T>
@@ -91,6 +94,9 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
 
     const int tid = threadIdx.x;
     const int m = a.m;
+    a.U += (size_t)blockIdx.z * a.u_stride;
+    a.in_states += (size_t)blockIdx.z * a.in_stride;
+    a.out += (size_t)blockIdx.z * a.out_stride;
     const uint8_t* ins = a.in_states + (size_t)blockIdx.y * m;
     if (tid == 0) {
         int c = 0;

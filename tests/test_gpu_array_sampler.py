@@ -99,7 +99,8 @@ def test_device_regime_matches_host_regime_statistically(lb, monkeypatch):
                 assert na == nb == 200_000
             keys = set(exact) | set(dev)
             tv = 0.5 * sum(abs(exact.get(k, 0) / na - dev.get(k, 0) / nb) for k in keys)
-            assert tv < 0.02, (mode, tv)
+            # two empirical distributions of N draws over K outcomes differ by about sqrt(K / (pi N)) in total variation
+            assert tv < 1.5 * np.sqrt(len(keys) / (np.pi * min(na, nb))) + 0.005, (mode, tv, len(keys))
             assert abs(na - nb) < 6 * np.sqrt(200_000) + 1
     finally:
         lb.uninstall()

@@ -183,3 +183,49 @@ def test_imperfect_source_combined_on_device(lw, name):
     for k, v in d2.items():
         assert d1[k] == pytest.approx(v, rel=1e-10, abs=1e-12 if k == vac else 1e-16)
     assert sum(dict(r1).values()) == 2000
+
+
+def test_batch_of_simulators_runs_as_one_launch(lw):
+    """lightworks.Batch across unitaries (sdk/tasks/batch.py:45-58, serial at backends/backend.py:102-103): a parameter
+    scan of Simulator tasks goes to the device as ONE launch with a table of unitaries and equals the task-by-task
+    results of the reference's CPU backend; mixed batches keep the reference's loop."""
+    import lightworks_b200
+    from lightworks.emulator import Backend
+
+    p = lw.Parameter(0.1)
+    circ = lw.PhotonicCircuit(6)
+    for i in range(5):
+        circ.bs(i, reflectivity=p)
+        circ.ps(i, 0.3 * i)
+    circ.add(lw.Unitary(lw.random_unitary(6, seed=3)))
+    values = [0.1, 0.25, 0.4, 0.55, 0.7, 0.85]
+    mk = lambda: lw.Batch(lw.Simulator, task_args=[[circ], [lw.State([1, 0, 1, 0, 1, 0])]],  # noqa: E731
+                          parameters={p: values})
+    ctx = lightworks_b200.default_context()
+    b = Backend("permanent")
+    l0 = ctx.launch_count()
+    got = b.run(mk())
+    launches = ctx.launch_count() - l0
+    ref = Backend("permanent_cpu").run(mk())
+    assert len(got) == len(ref) == len(values)
+    assert launches <= 2, launches  # fock_basis enumeration + ONE permanent launch for the six unitaries
+    for g, r in zip(got, ref):
+        assert g.outputs == r.outputs and g.inputs == r.inputs
+        assert _close(g.array, r.array)
+    assert not _close(got[0].array, got[-1].array)  # the parameter really changed the unitary
+    # explicit, differing outputs per task -> two groups; an Analyzer in the batch -> the reference's loop
+    batch = lw.Batch()
+    u = lw.Unitary(lw.random_unitary(4, seed=1))
+    batch.add(lw.Simulator(u, lw.State([1, 0, 1, 0]), lw.State([0, 1, 0, 1])))
+    batch.add(lw.Simulator(u, lw.State([1, 0, 1, 0]), lw.State([1, 1, 0, 0])))
+    batch.add(lw.Simulator(u, lw.State([1, 0, 1, 0])))
+    got = b.run(batch)
+    ref = Backend("permanent_cpu").run(batch)
+    for g, r in zip(got, ref):
+        assert g.outputs == r.outputs and _close(g.array, r.array)
+    mixed = lw.Batch()
+    mixed.add(lw.Simulator(u, lw.State([1, 0, 1, 0])))
+    mixed.add(lw.Analyzer(u, lw.State([1, 0, 1, 0])))
+    got = b.run(mixed)
+    assert [type(g).__name__ for g in got] == ["LazySimulationResult"] * 2
+    assert got[1].result_type == "probability"
