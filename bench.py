@@ -528,6 +528,14 @@ def main() -> int:  # noqa: PLR0915
                 line["extra"] = extras(ctx, stream, peak, d_U, torch, np, O, _lib)
             except Exception as e:  # the extras never take the headline line down with them
                 line["extra"] = {"error": repr(e)}
+            sl = line["extra"].get("slos_c3") if isinstance(line["extra"], dict) else None
+            if sl and "probabilities_per_s" in sl:
+                # second headline: the SAME distribution through the SLOS backend (Backend("slos")), HBM-bound
+                line["second_headline"] = {
+                    "metric": "output-state probabilities/sec (SLOS backend: complex128 state-vector evolution, full distribution)",
+                    "value": sl["probabilities_per_s"], "unit": UNIT, "ms_per_step": sl["ms"], "roofline": sl["roofline"],
+                    "kernel": "slos_units_kernel (K3u: prefix units, coalesced parent streams, parent block in shared memory) x 10 layers",
+                    "gather_kernel_ms": sl.get("gather_kernel_ms")}
     if rank == 0:
         emit(line)
     if world > 1:
@@ -568,11 +576,16 @@ def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
     ins = [1] * N_PH + [0] * (M - N_PH)
     with torch.cuda.stream(stream):
         d_p = torch.empty(S, dtype=torch.float64, device="cuda")
-    ms = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1))
+    ms = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1), reps=5)
+    _lib.set_option("slos_units", 0)  # the round-1 gather-form kernel beside it
+    try:
+        ms_gather = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1))
+    finally:
+        _lib.set_option("slos_units", 1)
     # algorithmic bytes: every layer reads its parent once and writes itself once (the last layer
     # writes 8-byte probabilities)
     slos_bytes = sum(16 * (comb(M + k - 2, k - 1) + comb(M + k - 1, k)) for k in range(1, N_PH + 1))
-    out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms,
+    out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms, "gather_kernel_ms": ms_gather,
                       "roofline": {"bound": "hbm", "achieved": slos_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes},
                       "gather_traffic": {"bytes": 16 * M * sum(comb(M + k - 2, k - 1) for k in range(1, N_PH + 1)),

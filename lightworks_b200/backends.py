@@ -189,9 +189,19 @@ class PermanentBackendMixin(_B200Base):
         return self.ctx.fock_basis(n_modes, n_photons).tolist()
 
     def state_generator_array(self, n_modes: int, n_photons: int) -> np.ndarray:
+        """fock_basis as a read-only uint8 array [S, m]; the last few are kept (a Batch asks for the same one per task)."""
         if n_photons == 0:
             return np.zeros((1, n_modes), dtype=np.uint8)
-        return self.ctx.fock_basis(n_modes, n_photons)
+        cache = self.__dict__.setdefault("_basis_cache", {})
+        arr = cache.get((n_modes, n_photons))
+        if arr is None:
+            arr = self.ctx.fock_basis(n_modes, n_photons)
+            arr.setflags(write=False)
+            if arr.nbytes <= 64 << 20:
+                if len(cache) >= 8:
+                    cache.pop(next(iter(cache)))
+                cache[(n_modes, n_photons)] = arr
+        return arr
 
     def probability_amplitude(self, unitary, input_state, output_state) -> complex:
         """permanent.py:53-83"""
@@ -567,6 +577,8 @@ def install(dtype: str = "complex128", device: int | None = None, patch_names: b
             return be.run_simulator_batch(tasks)
         return [self._run(t) for t in tasks]
 
+    # the dispatcher resolves annotations in module globals; Batch is local to install(), so hand it the class itself
+    _run_batch.__annotations__ = {"task": Batch}
     LwBackend._run.register(_run_batch)
 
     class B200SLOSBackend(SLOSBackendMixin, FockBackend):

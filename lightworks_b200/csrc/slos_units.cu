@@ -38,7 +38,13 @@ namespace lwb {
 constexpr int SU_THREADS = 256;
 constexpr int SU_DMAX = 8;        // trailing photons per unit (their modes are packed into one 64-bit word)
 constexpr int SU_NPMAX = 16;      // distinct prefix modes per unit
-constexpr uint32_t SU_TMAX = 8192;   // children per unit
+#ifndef LWB_SU_TMAX
+#define LWB_SU_TMAX 8192
+#endif
+#ifndef LWB_SU_MINB
+#define LWB_SU_MINB 3
+#endif
+constexpr uint32_t SU_TMAX = LWB_SU_TMAX;   // children per unit
 constexpr uint32_t SU_ITEM = 4096;   // a CTA takes consecutive units until it holds this many children ...
 constexpr uint32_t SU_ITEM_MIN = 256;  // ... fewer on small layers, so that every SM gets several CTAs
 static uint32_t item_size(uint64_t children) {
@@ -49,7 +55,7 @@ static uint32_t item_size(uint64_t children) {
 struct SlosUnit {
     uint64_t start;             // rank of the unit's first child in the child layer
     uint64_t pblock;            // rank of the first amplitude of B(P) in the parent layer
-    uint64_t sbase[SU_NPMAX];   // stream s: parent(c) = parent[sbase[s] + c]   (= pend - T)
+    uint64_t sbase[SU_NPMAX];   // stream s: parent(c) = parent[sbase[s] / 16 + c]: BYTE offset of (pend - T)
     uint32_t T, Tp;             // children; amplitudes of B(P)
     uint32_t lut;               // trailing modes of child c = lut_table[lut + c]
     uint8_t d, ell, np, has_ell;  // trailing photons; last prefix mode (0 if none); distinct prefix modes; l in prefix?
@@ -79,7 +85,15 @@ __device__ __forceinline__ double2 su_cmul_py(double2 a, double2 b) {  // CPytho
     return r;
 }
 
-constexpr int SU_R = 4;  // children per thread and pass (strided by the block size: every access stays coalesced)
+constexpr int SU_R = 2;  // children per thread and pass (strided by the block size: every access stays coalesced)
+
+__device__ __forceinline__ void su_cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void su_cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src));
+}
+__device__ __forceinline__ void su_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // Trailing part of one child, D trailing photons (compile-time: exact unrolling, constant shifts).  Terms in ascending
 // mode order; the run of mode l, if the prefix holds l, was merged into the last prefix term by the caller.
@@ -116,91 +130,153 @@ __device__ __forceinline__ void su_trailing(uint64_t y, uint32_t c, int ell, boo
     }
 }
 
-__global__ void __launch_bounds__(SU_THREADS) slos_units_kernel(SlosUnitsArgs a) {
+struct SuSmem {
+    const double2* ucol;
+    const double2* pb;
+    const double* sq;
+    const uint32_t* ht;
+    int mv;
+};
+
+// One pass over NJ * SU_THREADS children of the current unit.  Every global load is unconditional (indices clamped to the
+// unit) and issued ahead of its use: the trailing-mode table, then the prefix streams two streams ahead of the
+// arithmetic - the kernel is bound by the latency of these loads, not by their bandwidth (profiles/r02_k3u_*).
+template <int NJ>
+__device__ __forceinline__ void su_pass(const SlosUnitsArgs& a, const SlosUnit& un, const SuSmem& sm, uint32_t base, int tid,
+                                        bool* pb_ready) {
+    const uint32_t T = un.T;
+    const int d = un.d, np = un.np, ell = un.ell;
+    const bool has_ell = un.has_ell != 0;
+    const uint32_t ell4 = (uint32_t)ell * 0x01010101u;
+    uint32_t c[NJ];
+    uint64_t y[NJ];
+    double2 acc[NJ];
+    int lead[NJ];
+    const uint64_t* lut = a.lut + un.lut;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const uint32_t cj = base + j * SU_THREADS + tid;
+        c[j] = cj < T ? cj : T - 1;  // clamped: loads stay inside the unit, only the store is predicated
+        y[j] = lut[c[j]];
+    }
+    // ---- prefix modes, ascending: one end-aligned coalesced stream each.  Loads run two streams ahead of the
+    // arithmetic through three statically rotated buffers; sbase is a BYTE offset, so an address is one 64-bit add. ----
+    const char* pj[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        pj[j] = reinterpret_cast<const char*>(a.parent + c[j]);
+        acc[j] = make_double2(0.0, 0.0);
+        // trailing photons sitting in mode l extend the prefix's run of l (unused bytes of y are 0xff)
+        lead[j] = has_ell ? (__popc(__vcmpeq4((uint32_t)y[j], ell4)) + __popc(__vcmpeq4((uint32_t)(y[j] >> 32), ell4))) >> 3 : 0;
+    }
+    double2 b0[NJ], b1[NJ], b2[NJ];
+    auto load = [&](double2 (&buf)[NJ], int s) {
+        if (s < np) {
+            const uint64_t off = un.sbase[s];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) buf[j] = *reinterpret_cast<const double2*>(pj[j] + off);
+        }
+    };
+    auto use = [&](const double2 (&buf)[NJ], int s) {
+        if (s >= np) return;
+        const double2 uv = sm.ucol[un.pm[s]];
+        const int pmul = un.pmult[s];
+        if (s < np - 1) {  // multiplicity is the prefix's own: uniform for the whole unit
+            const bool scale = pmul > 1;
+            const double f = sm.sq[pmul];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                double2 v = buf[j];
+                if (scale) { v.x = __dmul_rn(f, v.x); v.y = __dmul_rn(f, v.y); }
+                const double2 term = su_cmul_py(v, uv);
+                acc[j].x = __dadd_rn(acc[j].x, term.x);
+                acc[j].y = __dadd_rn(acc[j].y, term.y);
+            }
+        } else {  // the last prefix mode is l: trailing photons in l add to its multiplicity, child by child
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int mult = pmul + lead[j];
+                double2 v = buf[j];
+                if (mult > 1) {
+                    const double f = sm.sq[mult];
+                    v.x = __dmul_rn(f, v.x);
+                    v.y = __dmul_rn(f, v.y);
+                }
+                const double2 term = su_cmul_py(v, uv);
+                acc[j].x = __dadd_rn(acc[j].x, term.x);
+                acc[j].y = __dadd_rn(acc[j].y, term.y);
+            }
+        }
+    };
+    load(b0, 0);
+    load(b1, 1);
+    for (int s = 0; s < np; s += 3) {
+        load(b2, s + 2);
+        use(b0, s);
+        load(b0, s + 3);
+        use(b1, s + 1);
+        load(b1, s + 4);
+        use(b2, s + 2);
+    }
+    if (!*pb_ready) {  // first pass of the unit: the parent block was copied asynchronously behind the streams
+        su_cp_async_wait();
+        __syncthreads();
+        *pb_ready = true;
+    }
+    // ---- trailing modes, ascending: parents inside the staged block B(P) ----
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        switch (d) {  // block-uniform
+            case 1: su_trailing<1>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            case 2: su_trailing<2>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            case 3: su_trailing<3>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            case 4: su_trailing<4>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            case 5: su_trailing<5>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            case 6: su_trailing<6>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            case 7: su_trailing<7>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+            default: su_trailing<8>(y[j], c[j], ell, has_ell, sm.ht, sm.mv, sm.pb, sm.ucol, sm.sq, acc[j]); break;
+        }
+        if (base + j * SU_THREADS + tid < T) {
+            const uint64_t rank = un.start + c[j];
+            if (a.write_probs)  // abs(a) ** 2 (slos.py:74); x*x + y*y differs from hypot(x, y)^2 by <= 2 ulp
+                reinterpret_cast<double*>(a.child)[rank] = __dadd_rn(__dmul_rn(acc[j].x, acc[j].x), __dmul_rn(acc[j].y, acc[j].y));
+            else
+                reinterpret_cast<double2*>(a.child)[rank] = acc[j];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(SU_THREADS, LWB_SU_MINB) slos_units_kernel(SlosUnitsArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int m = a.m, mv = m + 1;
     double2* ucol = reinterpret_cast<double2*>(smem_raw);                 // [m]
     double2* pb = ucol + m;                                               // [max_tp] parent block
     double* sq = reinterpret_cast<double*>(pb + a.max_tp);                // [k + 1] (+ pad)
     uint32_t* ht = reinterpret_cast<uint32_t*>(sq + ((a.k + 2) & ~1));    // [SU_DMAX][mv]
-    __shared__ SlosUnit un;
+    __shared__ __align__(16) SlosUnit un2[2];  // current unit and the prefetched next one
     const int tid = threadIdx.x;
     for (int e = tid; e < m; e += SU_THREADS) ucol[e] = a.U[(size_t)e * m + a.in_mode];
     for (int e = tid; e <= a.k; e += SU_THREADS) sq[e] = a.sqrt_tab[e];
     for (int e = tid; e < SU_DMAX * mv; e += SU_THREADS) ht[e] = a.ht[e];
     const uint2 item = a.items[blockIdx.x];
-    for (uint32_t u = item.x; u < item.y; ++u) {
-        __syncthreads();  // previous unit done with `un` and `pb` (first pass: the tables are written)
-        if (tid < (int)(sizeof(SlosUnit) / 4))
-            reinterpret_cast<uint32_t*>(&un)[tid] = reinterpret_cast<const uint32_t*>(a.units + u)[tid];
-        __syncthreads();
+    constexpr int UW = (int)(sizeof(SlosUnit) / 4);
+    if (tid < UW) su_cp_async4(reinterpret_cast<uint32_t*>(&un2[0]) + tid, reinterpret_cast<const uint32_t*>(a.units + item.x) + tid);
+    SuSmem sm{ucol, pb, sq, ht, mv};
+    int cur = 0;
+    for (uint32_t u = item.x; u < item.y; ++u, cur ^= 1) {
+        su_cp_async_wait();
+        __syncthreads();  // unit descriptor `cur` has arrived; everybody is done with the previous unit's `pb`
+        const SlosUnit& un = un2[cur];
+        if (u + 1 < item.y && tid < UW)  // prefetch the next descriptor behind this unit's work
+            su_cp_async4(reinterpret_cast<uint32_t*>(&un2[cur ^ 1]) + tid, reinterpret_cast<const uint32_t*>(a.units + u + 1) + tid);
+        // parent block -> shared memory, asynchronously: only the trailing part needs it, after the prefix streams
         const uint32_t T = un.T, Tp = un.Tp;
         const double2* pblk = a.parent + un.pblock;
-        for (uint32_t i = tid; i < Tp; i += SU_THREADS) pb[i] = pblk[i];
-        __syncthreads();
-        const int d = un.d, np = un.np, ell = un.ell;
-        const bool has_ell = un.has_ell != 0;
-        const uint64_t* lut = a.lut + un.lut;
-        const uint32_t ell4 = (uint32_t)ell * 0x01010101u;
+        for (uint32_t i = tid; i < Tp; i += SU_THREADS) su_cp_async16(pb + i, pblk + i);
+        bool pb_ready = false;
         for (uint32_t base = 0; base < T; base += SU_THREADS * SU_R) {
-            // SU_R children per thread, strided by the block size: child j of this thread is c0 + j * SU_THREADS
-            const uint32_t c0 = base + tid;
-            uint64_t y[SU_R];
-            double2 acc[SU_R];
-            int lead[SU_R];
-#pragma unroll
-            for (int j = 0; j < SU_R; ++j) {
-                const uint32_t c = c0 + j * SU_THREADS;
-                y[j] = c < T ? lut[c] : ~0ull;
-                acc[j] = make_double2(0.0, 0.0);
-                // trailing photons sitting in mode l extend the prefix's run of l (unused bytes of y are 0xff)
-                lead[j] = has_ell ? (__popc(__vcmpeq4((uint32_t)y[j], ell4)) + __popc(__vcmpeq4((uint32_t)(y[j] >> 32), ell4))) >> 3 : 0;
-            }
-            // ---- prefix modes, ascending: one end-aligned coalesced stream each; constants hoisted per stream ----
-            for (int s = 0; s < np; ++s) {
-                const double2 uv = ucol[un.pm[s]];
-                const int pmul = un.pmult[s];
-                const bool last_stream = s == np - 1;  // the only prefix mode that can equal l
-                const double2* __restrict__ sp = a.parent + un.sbase[s] + c0;
-#pragma unroll
-                for (int j = 0; j < SU_R; ++j) {
-                    if (c0 + j * SU_THREADS < T) {
-                        double2 t = sp[j * SU_THREADS];
-                        const int mult = pmul + (last_stream ? lead[j] : 0);
-                        if (mult > 1) {
-                            const double f = sq[mult];
-                            t.x = __dmul_rn(f, t.x);
-                            t.y = __dmul_rn(f, t.y);
-                        }
-                        const double2 term = su_cmul_py(t, uv);
-                        acc[j].x = __dadd_rn(acc[j].x, term.x);
-                        acc[j].y = __dadd_rn(acc[j].y, term.y);
-                    }
-                }
-            }
-            // ---- trailing modes, ascending: parents inside the staged block B(P) ----
-#pragma unroll
-            for (int j = 0; j < SU_R; ++j) {
-                const uint32_t c = c0 + j * SU_THREADS;
-                if (c < T) {
-                    switch (d) {  // block-uniform
-                        case 1: su_trailing<1>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        case 2: su_trailing<2>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        case 3: su_trailing<3>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        case 4: su_trailing<4>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        case 5: su_trailing<5>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        case 6: su_trailing<6>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        case 7: su_trailing<7>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                        default: su_trailing<8>(y[j], c, ell, has_ell, ht, mv, pb, ucol, sq, acc[j]); break;
-                    }
-                    const uint64_t rank = un.start + c;
-                    if (a.write_probs)  // abs(a) ** 2 (slos.py:74); x*x + y*y differs from hypot(x, y)^2 by <= 2 ulp
-                        reinterpret_cast<double*>(a.child)[rank] =
-                            __dadd_rn(__dmul_rn(acc[j].x, acc[j].x), __dmul_rn(acc[j].y, acc[j].y));
-                    else
-                        reinterpret_cast<double2*>(a.child)[rank] = acc[j];
-                }
-            }
+            if (T - base > SU_THREADS) su_pass<2>(a, un, sm, base, tid, &pb_ready);
+            else su_pass<1>(a, un, sm, base, tid, &pb_ready);
         }
     }
 }
@@ -276,7 +352,7 @@ struct Builder {
                 if (t != i) y[q++] = x[t];          // drop one copy of mode x[i]
             for (int t = 0; t < d; ++t) y[q++] = m - 1;  // last state of the shortened prefix's subtree
             const uint64_t pend = lex_rank(bin, y, k - 1, m) + 1;
-            u.sbase[np] = pend - u.T;
+            u.sbase[np] = (pend - u.T) * 16;  // byte offset into the parent layer
             ++np;
             i = j;
         }
@@ -417,7 +493,7 @@ int slos_units_plan_check(int m, int k, uint64_t* children_checked) {
                 int q = 0;
                 for (int t = 0; t < k; ++t)
                     if (t != at) y[q++] = x[t];
-                if (lex_rank(bin, y, k - 1, m) != u.sbase[s] + c) return LWB_E_ARG;
+                if (u.sbase[s] % 16 || lex_rank(bin, y, k - 1, m) != u.sbase[s] / 16 + c) return LWB_E_ARG;
             }
             uint32_t Q = 0;
             int prev = u.ell;
