@@ -130,7 +130,7 @@ class _B200Base:
 
     @property
     def ctx(self) -> _lib.Context:
-        if self._ctx is None:
+        if self._ctx is None or not self._ctx.handle:  # a context borrowed from a closed communicator is dead: resolve again
             comm = local_comm() if self._device is None else None
             # with a LOCAL communicator device 0's context is the communicator's own (one set of buffers per device)
             self._ctx = comm.context(0) if comm is not None else _lib.default_context(self._device)

@@ -26,6 +26,16 @@
 #define LWB_MAX_MODES 128
 #define LWB_MAX_PHOTONS 40
 
+/* Debug build (make TAG=bounds EXTRA=-DLWB_DEBUG_BOUNDS): device-side index asserts in the kernels that compute their
+ * own addresses.  compute-sanitizer is closed on the measurement pool, so tools/bounds_check.sh runs the small
+ * configurations (tools/sanitize_small.py) against this build instead. */
+#ifdef LWB_DEBUG_BOUNDS
+#include <assert.h>
+#define LWB_BOUNDS(cond) assert(cond)
+#else
+#define LWB_BOUNDS(cond) ((void)0)
+#endif
+
 #define LWB_MAX_PEERS 15 /* extra destinations of a probability store: the other GPUs of one NVLink domain */
 
 namespace lwb {

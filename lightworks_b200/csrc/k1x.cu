@@ -366,17 +366,23 @@ static int make_plan(K1xState* st, int n, Plan** out, std::string* err) {
 
 template <int N>
 struct K1xTable {  // n below the static range: the generic walk only
-    static void fill(K1xFn* t) { t[N] = k1x_fused_kernel<N, false>; K1xTable<N - 1>::fill(t); }
+    static void fill(K1xFn (*t)[2]) {
+        t[N][0] = k1x_fused_kernel<N, false, double>;
+        t[N][1] = k1x_fused_kernel<N, false, float>;
+        K1xTable<N - 1>::fill(t);
+    }
 };
 template <>
 struct K1xTable<1> {
-    static void fill(K1xFn*) {}
+    static void fill(K1xFn (*)[2]) {}
 };
+
+bool k1x_supported_dtype(int n, int dtype) { return k1x_supported(n) && (dtype == 0 || n <= K1X_C64_MAX_N); }
 
 int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, const double2* d_U, int m,
                     const uint8_t* d_in_state, int n, uint64_t r0, uint64_t cnt, double* d_probs, uint64_t* launches,
-                    std::string* err, const MirrorSet* mirrors) {
-    static K1xFn table[K1X_MAX_N + 1];
+                    std::string* err, const MirrorSet* mirrors, int dtype) {
+    static K1xFn table[K1X_MAX_N + 1][2];
     static std::once_flag table_once;  // contexts of several GPUs may make their first call concurrently
     std::call_once(table_once, [] {
         K1xTable<K1X_STATIC_MIN_N - 1>::fill(table);
@@ -384,10 +390,10 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
         for (auto g : groups) {
             int c = 0;
             const K1xStaticEntry* e = g(&c);
-            for (int i = 0; i < c; ++i) table[e[i].n] = e[i].fn;
+            for (int i = 0; i < c; ++i) { table[e[i].n][0] = e[i].fn[0]; table[e[i].n][1] = e[i].fn[1]; }
         }
     });
-    if (!k1x_supported(n) || !table[n] || cnt >= (1ull << 32)) { *err = "k1x: unsupported size"; return LWB_E_LIMIT; }
+    if (dtype < 0 || dtype > 1 || !k1x_supported(n) || !table[n][dtype] || cnt >= (1ull << 32)) { *err = "k1x: unsupported size"; return LWB_E_LIMIT; }
     if (cnt == 0) return 0;
     Plan* pl = nullptr;
     int rc = make_plan(st, n, &pl, err);
@@ -430,11 +436,11 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
     K1xArgs ka;
     ka.bin = d_bin; ka.U = d_U; ka.m = m; ka.in_state = d_in_state; ka.r0 = r0; ka.meta = pl->d_meta; ka.prog = pl->d_prog;
     ka.layout = pl->d_layout; ka.bstart = st->d_bstart; ka.offsets = st->d_offsets; ka.counts = st->d_counts;
-    ka.n_types = pl->n_types; ka.bucket = st->d_bucket; ka.probs = d_probs;
+    ka.n_types = pl->n_types; ka.bucket = st->d_bucket; ka.cnt = (uint32_t)cnt; ka.probs = d_probs;
     ka.mir.n = 0;
     if (mirrors) ka.mir = *mirrors;
-    const size_t smem = (size_t)m * (n | 1) * 16 + (size_t)n * tb * 4;
-    K1xFn fn = table[n];
+    const size_t smem = (size_t)m * (n | 1) * (dtype ? 8 : 16) + (size_t)n * tb * 4;
+    K1xFn fn = table[n][dtype];
     if (smem > 48 * 1024) K1X_CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t grid = (cnt + tb - 1) / tb + (uint64_t)pl->n_types;
     fn<<<(unsigned)grid, tb, smem, stream>>>(ka);

@@ -26,6 +26,7 @@ struct K1xState;  // cached plans + scratch buffers (owned by the context)
 K1xState* k1x_create();
 void k1x_destroy(K1xState* st);
 bool k1x_supported(int n);
+bool k1x_supported_dtype(int n, int dtype);  // dtype 0 complex128, 1 complex64 (n <= 12: drift of the float column sums)
 int k1x_plan_info(int n, int t, int* n_types, int* s_out, int* d_out, int* T_out, int* factor_out, double* abs_coef_sum);
 
 // probs[k] = |<basis[r0+k]|U|in>|^2 for k in [0, cnt), all pointers on the device; enqueues five kernels on
@@ -33,6 +34,6 @@ int k1x_plan_info(int n, int t, int* n_types, int* s_out, int* d_out, int* T_out
 // Returns 0, or a negative LWB_E_* code with *err set.
 int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, const double2* d_U, int m,
                     const uint8_t* d_in_state, int n, uint64_t r0, uint64_t cnt, double* d_probs, uint64_t* launches,
-                    std::string* err, const MirrorSet* mirrors = nullptr);
+                    std::string* err, const MirrorSet* mirrors = nullptr, int dtype = 0);
 
 }  // namespace lwb

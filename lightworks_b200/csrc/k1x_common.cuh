@@ -17,7 +17,7 @@ namespace lwb {
 // 256-thread blocks per SM in 128 registers; beyond that the walks want ~250 registers and two 128-thread blocks
 // stagger their prologues and tails better than one 256-thread block (6 % at n = 12, 3 % at n = 14).
 #ifndef K1X_BLOCK
-#define K1X_BLOCK(N) ((N) <= 10 ? 256 : 128)
+#define K1X_BLOCK(N) 128  /* round 2: n <= 10 runs 128 threads x 3 blocks/SM (168 registers, no spills): -1.1 % at C3 */
 #endif
 constexpr int k1x_unroll = K1X_UNROLL;
 __host__ __device__ constexpr int k1x_threads(int n) { return K1X_BLOCK(n); }
@@ -57,6 +57,7 @@ struct K1xArgs {
     const uint32_t* counts;   // [n_types], indexed by type
     int n_types;
     const uint32_t* bucket;
+    uint32_t cnt;  // states of the rank range (debug bounds checks)
     double* probs;
     MirrorSet mir;  // peers that receive every probability as it is produced (multi-GPU: no gather step afterwards)
 };
@@ -70,31 +71,38 @@ struct K1xArgs {
 #define K1XS_MINB(N) ((N) <= 10 ? 2 : 0)
 #endif
 
-template <int TB>
+template <int TB, typename T>
 struct K1xLane {   // what the prologue hands to the walk of one permanent
-    uint32_t vs_base;  // shared-memory address of the U[:, input columns] table, row stride NP * 16 bytes
-    const int* srow;   // [N][TB]: row offset (in double2) of slot sl for lane tid at srow[sl * TB + tid]
+    uint32_t vs_base;  // shared-memory address of the U[:, input columns] table, row stride NP complex entries
+    const int* srow;   // [N][TB]: row offset (in complex entries) of slot sl for lane tid at srow[sl * TB + tid]
     int tid;
-    __device__ __forceinline__ uint32_t slot_addr(int sl) const { return vs_base + 16u * (uint32_t)srow[sl * TB + tid]; }
+    __device__ __forceinline__ uint32_t slot_addr(int sl) const {
+        return vs_base + (uint32_t)(2 * sizeof(T)) * (uint32_t)srow[sl * TB + tid];
+    }
 };
 
-__device__ __forceinline__ double2 k1x_ld(uint32_t addr, int j) {
+__device__ __forceinline__ double2 k1x_ld(uint32_t addr, int j, double) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr + 16u * j));
     return v;
 }
+__device__ __forceinline__ float2 k1x_ld(uint32_t addr, int j, float) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr + 8u * j));
+    return v;
+}
 
 // start tuple v = 0 (every copy of every row '+'):  w_j = 1/2 sum_i s_i a_{r_i j}
-template <int N>
-__device__ __forceinline__ void k1x_start(const K1xLane<k1x_threads(N)>& ln, const TypeMeta& tm, double (&wr)[N], double (&wi)[N]) {
+template <int N, typename T>
+__device__ __forceinline__ void k1x_start(const K1xLane<k1x_threads(N), T>& ln, const TypeMeta& tm, T (&wr)[N], T (&wi)[N]) {
 #pragma unroll
-    for (int j = 0; j < N; ++j) { wr[j] = 0.0; wi[j] = 0.0; }
+    for (int j = 0; j < N; ++j) { wr[j] = T(0); wi[j] = T(0); }
     for (int sl = 0; sl < tm.d; ++sl) {
-        const double c = 0.5 * (double)tm.s[sl];
+        const T c = T(0.5) * (T)tm.s[sl];
         const uint32_t ra = ln.slot_addr(sl);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            const double2 v = k1x_ld(ra, j);
+            const auto v = k1x_ld(ra, j, T());
             wr[j] = fma(c, v.x, wr[j]);
             wi[j] = fma(c, v.y, wi[j]);
         }
@@ -105,27 +113,28 @@ __device__ __forceinline__ void k1x_start(const K1xLane<k1x_threads(N)>& ln, con
 // Generic table-driven walk: every tuple of every row is one Step of the program.  The step descriptor and this
 // lane's row address are fetched one term ahead, and the row of a flip is loaded BEFORE the product chain of the
 // same term, so the shared-memory latency hides behind ~40 FP64 instructions instead of stalling the adds.
-template <int N>
-__device__ __forceinline__ void k1x_generic_walk(const K1xLane<k1x_threads(N)>& ln, const TypeMeta& tm, const Step* __restrict__ prog,
+template <int N, typename T>
+__device__ __forceinline__ void k1x_generic_walk(const K1xLane<k1x_threads(N), T>& ln, const TypeMeta& tm, const Step* __restrict__ prog,
                                                  double& sr, double& si) {
-    double wr[N], wi[N];
-    k1x_start<N>(ln, tm, wr, wi);
-    const int T = tm.T;
+    using V = typename vec2<T>::type;
+    T wr[N], wi[N];
+    k1x_start<N, T>(ln, tm, wr, wi);
+    const int n_steps = tm.T;
     sr = 0.0;
     si = 0.0;
     Step st = prog[0];  // same address for every lane of the block: one broadcast load
     uint32_t rowaddr = ln.slot_addr(st.slot);
 #pragma unroll k1x_unroll
-    for (int t = 0; t < T; ++t) {
-        const Step nx = prog[t + 1 < T ? t + 1 : t];
+    for (int t = 0; t < n_steps; ++t) {
+        const Step nx = prog[t + 1 < n_steps ? t + 1 : t];
         const uint32_t nrowaddr = ln.slot_addr(nx.slot);
-        double2 rv[N];
+        V rv[N];
 #pragma unroll
-        for (int j = 0; j < N; ++j) rv[j] = k1x_ld(rowaddr, j);
-        double pr, pi;
-        cprod<N, double>(wr, wi, pr, pi);
-        sr = fma(st.coef, pr, sr);
-        si = fma(st.coef, pi, si);
+        for (int j = 0; j < N; ++j) rv[j] = k1x_ld(rowaddr, j, T());
+        T pr, pi;
+        cprod<N, T>(wr, wi, pr, pi);
+        sr = fma(st.coef, (double)pr, sr);  // the weighted sum is kept in double for both precisions
+        si = fma(st.coef, (double)pi, si);
         // v_slot += dir  =>  (s - 2v)/2 decreases by dir   (the update after the last term is harmless)
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -145,36 +154,36 @@ __device__ __forceinline__ void k1x_generic_walk(const K1xLane<k1x_threads(N)>& 
 // where chunk t-1 ended, so it is exactly Gray chunk q = t of glynn_chunk (only the parity of t matters) and needs
 // no new start vector.  The program's coefficient carries the binomials and signs of the bunched tuple and the
 // parity sign of the chunk.
-template <int N, int C>
-__device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N)>& ln, const TypeMeta& tm, const Step* __restrict__ prog,
+template <int N, int C, typename T>
+__device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N), T>& ln, const TypeMeta& tm, const Step* __restrict__ prog,
                                                 double& sr, double& si) {
     static_assert(C >= 2 && C <= N - 1, "static walk needs at least 3 single rows");
     constexpr int U = C < K1XS_U(N) ? C : K1XS_U(N);
     const int d = tm.d;  // distinct rows; slots [0, d-C-1) bunched, then C+1 singles in ascending mode order
-    double wr[N], wi[N];
-    k1x_start<N>(ln, tm, wr, wi);
+    T wr[N], wi[N];
+    k1x_start<N, T>(ln, tm, wr, wi);
     // Gray bit k <-> slot d-1-k: the highest modes flip fastest (the ones neighbouring lanes share, so their
     // shared-memory reads mostly broadcast); slot d-1-C is the fixed '+' single.  (Keeping the two fastest rows in
     // registers instead was measured: no gain, the kernel is not bound by shared-memory bandwidth.)
     uint32_t lowaddr[U];
 #pragma unroll
     for (int k = 0; k < U; ++k) lowaddr[k] = ln.slot_addr(d - 1 - k);
-    const int T = tm.T;
+    const int n_steps = tm.T;
     sr = 0.0;
     si = 0.0;
     constexpr uint32_t NBLK = 1u << (C - U);
     constexpr int BLK = 1 << U;
 #pragma unroll 1
-    for (int t = 0; t < T; ++t) {
+    for (int t = 0; t < n_steps; ++t) {
         const Step st = prog[t];
         const uint32_t par = (uint32_t)t & 1u;
-        double cr = 0.0, ci = 0.0;
+        T cr = T(0), ci = T(0);
 #pragma unroll 1
         for (uint32_t ob = 0; ob < NBLK; ++ob) {
 #pragma unroll
             for (int tt = 0; tt < BLK; ++tt) {
-                double pr, pi;
-                cprod<N, double>(wr, wi, pr, pi);
+                T pr, pi;
+                cprod<N, T>(wr, wi, pr, pi);
                 if (tt & 1) { cr -= pr; ci -= pi; }
                 else { cr += pr; ci += pi; }
                 if (tt + 1 < BLK) {
@@ -184,16 +193,16 @@ __device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N)>& l
                         const bool newbit = ((t1 >> k) ^ (t1 >> (k + 1))) & 1;
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
-                            const double2 v = k1x_ld(lowaddr[k], j);
+                            const auto v = k1x_ld(lowaddr[k], j, T());
                             if (newbit) { wr[j] -= v.x; wi[j] -= v.y; }
                             else { wr[j] += v.x; wi[j] += v.y; }
                         }
                     } else {  // k == U-1: bit U of the step index decides
                         const uint32_t hi = (U == C) ? par : (ob & 1u);
-                        const double sg = hi ? 1.0 : -1.0;
+                        const T sg = hi ? T(1) : T(-1);
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
-                            const double2 v = k1x_ld(lowaddr[k], j);
+                            const auto v = k1x_ld(lowaddr[k], j, T());
                             wr[j] = fma(sg, v.x, wr[j]);
                             wi[j] = fma(sg, v.y, wi[j]);
                         }
@@ -204,24 +213,24 @@ __device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N)>& l
                 const uint32_t o1 = ob + 1;
                 const int k = U + (__ffs(o1) - 1);
                 const uint32_t newbit = (k == C - 1) ? (1u ^ par) : (((o1 >> (k - U)) ^ (o1 >> (k - U + 1))) & 1u);
-                const double sg = newbit ? -1.0 : 1.0;
+                const T sg = newbit ? T(-1) : T(1);
                 const uint32_t ra = ln.slot_addr(d - 1 - k);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const double2 v = k1x_ld(ra, j);
+                    const auto v = k1x_ld(ra, j, T());
                     wr[j] = fma(sg, v.x, wr[j]);
                     wi[j] = fma(sg, v.y, wi[j]);
                 }
             }
         }
-        sr = fma(st.coef, cr, sr);
-        si = fma(st.coef, ci, si);
-        if (t + 1 < T) {  // next tuple of the bunched rows: v_slot += dir  =>  w -= dir * row
-            const double sg = st.dir > 0 ? -1.0 : 1.0;
+        sr = fma(st.coef, (double)cr, sr);  // chunk sums join the double accumulator
+        si = fma(st.coef, (double)ci, si);
+        if (t + 1 < n_steps) {  // next tuple of the bunched rows: v_slot += dir  =>  w -= dir * row
+            const T sg = st.dir > 0 ? T(-1) : T(1);
             const uint32_t ra = ln.slot_addr(st.slot);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
-                const double2 v = k1x_ld(ra, j);
+                const auto v = k1x_ld(ra, j, T());
                 wr[j] = fma(sg, v.x, wr[j]);
                 wi[j] = fma(sg, v.y, wi[j]);
             }
@@ -230,32 +239,33 @@ __device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N)>& l
 }
 
 // klass C >= 2 -> k1x_static_walk<N, C>, anything else -> the generic walk (block-uniform branch)
-template <int N, int C>
+template <int N, int C, typename T>
 struct K1xDispatch {
-    static __device__ __forceinline__ void run(int klass, const K1xLane<k1x_threads(N)>& ln, const TypeMeta& tm, const Step* prog,
+    static __device__ __forceinline__ void run(int klass, const K1xLane<k1x_threads(N), T>& ln, const TypeMeta& tm, const Step* prog,
                                                double& sr, double& si) {
-        if (klass == C) k1x_static_walk<N, C>(ln, tm, prog, sr, si);
-        else K1xDispatch<N, C - 1>::run(klass, ln, tm, prog, sr, si);
+        if (klass == C) k1x_static_walk<N, C, T>(ln, tm, prog, sr, si);
+        else K1xDispatch<N, C - 1, T>::run(klass, ln, tm, prog, sr, si);
     }
 };
-template <int N>
-struct K1xDispatch<N, 1> {
-    static __device__ __forceinline__ void run(int, const K1xLane<k1x_threads(N)>& ln, const TypeMeta& tm, const Step* prog, double& sr,
+template <int N, typename T>
+struct K1xDispatch<N, 1, T> {
+    static __device__ __forceinline__ void run(int, const K1xLane<k1x_threads(N), T>& ln, const TypeMeta& tm, const Step* prog, double& sr,
                                                double& si) {
-        k1x_generic_walk<N>(ln, tm, prog, sr, si);
+        k1x_generic_walk<N, T>(ln, tm, prog, sr, si);
     }
 };
 
 // One block = up to 256 permanents of ONE multiplicity pattern, one thread per permanent.  Block b finds its
 // pattern by a binary search of the device-built block table, so the whole pipeline needs no host round trip and a
 // single launch covers every pattern (grid = upper bound, surplus blocks leave at once).
-template <int N, bool STATIC>
+template <int N, bool STATIC, typename T>
 __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
+    using V = typename vec2<T>::type;
     constexpr int TB = k1x_threads(N);
     if (blockIdx.x >= a.bstart[a.n_types]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NP = N | 1;  // odd row stride (in 16-byte units): lanes reading different rows spread over the banks
-    double2* Vs = reinterpret_cast<double2*>(smem_raw);         // [m][NP]
+    constexpr int NP = N | 1;  // odd row stride (in complex entries): lanes reading different rows spread over the banks
+    V* Vs = reinterpret_cast<V*>(smem_raw);                     // [m][NP]
     int* srow = reinterpret_cast<int*>(Vs + (size_t)a.m * NP);  // [N][TB] row offsets per slot
     __shared__ int incol[N];
     __shared__ double fin_s;
@@ -296,7 +306,11 @@ __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
     __syncthreads();
     for (int e = tid; e < m * N; e += TB) {
         const int r = e / N, c = e - r * N;
-        Vs[r * NP + c] = a.U[(size_t)r * m + incol[c]];
+        const double2 u = a.U[(size_t)r * m + incol[c]];
+        V v;
+        v.x = (T)u.x;
+        v.y = (T)u.y;
+        Vs[r * NP + c] = v;
     }
     __syncthreads();
     const uint32_t item = range[0] + tid;
@@ -320,37 +334,46 @@ __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
         }
         for (int sl = 0; sl < nd; ++sl) srow[sl * TB + tid] = mode[sl] * NP;
     }
-    K1xLane<TB> ln;
+    K1xLane<TB, T> ln;
     ln.vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
     ln.srow = srow;
     ln.tid = tid;
     double sr, si;
-    K1xDispatch<N, STATIC ? N - 1 : 1>::run(tm.klass, ln, tm, a.prog + tm.prog_off, sr, si);
+    K1xDispatch<N, STATIC ? N - 1 : 1, T>::run(tm.klass, ln, tm, a.prog + tm.prog_off, sr, si);
     const double scale = sqrt(fin_s * fout);
     const double f = (double)tm.factor;
     const double re = (f * sr) / scale, im = (f * si) / scale;
     const double pr_out = re * re + im * im;
+    LWB_BOUNDS(k_out < a.cnt);
     a.probs[k_out] = pr_out;
     for (int g = 0; g < a.mir.n; ++g) a.mir.p[g][k_out] = pr_out;  // fire-and-forget stores into peer memory
 }
 
 // (launch bounds: an explicit minBlocks of 1 makes ptxas schedule the walk ~25 % slower than none on B200)
-template <int N, bool STATIC>
-__global__ void __launch_bounds__(k1x_threads(N)) k1x_fused_kernel(K1xArgs a) { k1x_block<N, STATIC>(a); }
-template <int N, bool STATIC>
-__global__ void __launch_bounds__(k1x_threads(N), 2 * (256 / k1x_threads(N))) k1x_fused_kernel_2(K1xArgs a) { k1x_block<N, STATIC>(a); }
+template <int N, bool STATIC, typename T>
+__global__ void __launch_bounds__(k1x_threads(N)) k1x_fused_kernel(K1xArgs a) { k1x_block<N, STATIC, T>(a); }
+#ifndef K1XS_BLOCKS_PER_SM
+#define K1XS_BLOCKS_PER_SM(N) 3
+#endif
+template <int N, bool STATIC, typename T>
+__global__ void __launch_bounds__(k1x_threads(N), K1XS_BLOCKS_PER_SM(N)) k1x_fused_kernel_2(K1xArgs a) { k1x_block<N, STATIC, T>(a); }
+
+// complex64 walks keep the 1e-4 promise only while one Gray chunk stays short (drift of the float column sums,
+// see glynn_chunk_acc): the float kernels exist for n <= K1X_C64_MAX_N, beyond it complex64 uses the expanded-row kernel
+constexpr int K1X_C64_MAX_N = 12;
 
 typedef void (*K1xFn)(K1xArgs);
 struct K1xStaticEntry {
     int n;
-    K1xFn fn;
+    K1xFn fn[2];  // [dtype]: complex128, complex64 (nullptr above K1X_C64_MAX_N)
 };
-template <int N>
+template <int N, typename T>
 constexpr K1xFn k1x_static_fn() {
-    if constexpr (K1XS_MINB(N) == 2) return k1x_fused_kernel_2<N, true>;
-    else return k1x_fused_kernel<N, true>;
+    if constexpr (sizeof(T) == 4 && N > K1X_C64_MAX_N) return nullptr;
+    else if constexpr (K1XS_MINB(N) == 2) return k1x_fused_kernel_2<N, true, T>;
+    else return k1x_fused_kernel<N, true, T>;
 }
-#define LWB_K1XS_ENTRY(N) {N, k1x_static_fn<N>()}
+#define LWB_K1XS_ENTRY(N) {N, {k1x_static_fn<N, double>(), k1x_static_fn<N, float>()}}
 
 const K1xStaticEntry* k1xs_g0_table(int* count);
 const K1xStaticEntry* k1xs_g1_table(int* count);

@@ -386,12 +386,12 @@ int lwb::launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* d_
     if (m < 1 || m > LWB_MAX_MODES) return fail(LWB_E_LIMIT, "modes m=%d outside [1,%d]", m, LWB_MAX_MODES);
     if (n_in < 1 || n_in > 65535) return fail(LWB_E_ARG, "n_in=%d outside [1,65535]", n_in);
     if (n_out == 0) return 0;
-    if (g_multiplicity_aware && !d_outs && n_in == 1 && want_probs && dtype == LWB_C128 && k1x_supported(n) &&
-        n >= 7 && n_out < (1ull << 32)) {  // by n only: a rank-range shard is bit-identical to the same slice of the whole
+    if (g_multiplicity_aware && !d_outs && n_in == 1 && want_probs && k1x_supported_dtype(n, dtype) &&
+        n >= 7 && n_out < (1ull << 32)) {  // by n and dtype only: a rank-range shard is bit-identical to the same slice of the whole
         // full-basis rank range: bunched output states repeat rows, walk prod(s_i+1)/2 terms instead of 2^(n-1)
         std::string err;
         int rc = k1x_basis_probs(h->k1x, h->stream, h->d_bin, (const double2*)d_U, m, d_ins, n, r0, n_out, d_out,
-                                 &h->launches, &err, &h->mirror);
+                                 &h->launches, &err, &h->mirror, dtype);
         if (rc) return fail(rc, "%s", err.c_str());
         return 0;
     }
@@ -545,7 +545,12 @@ int lwb_perm_basis_probs(lwb_handle h, const double* U, int m, const uint8_t* in
     // kernels of piece c+1 and only the small last copy is exposed (the copy is the only host<->device traffic of
     // this path: 8 bytes per state).  Few pieces: every piece pays the bucketing passes of the multiplicity-aware walk.
     static const double cut[5] = {0.0, 0.40, 0.70, 0.90, 1.0};
-    const int chunks = cnt >= (4u << 20) ? 4 : 1;
+    // ... but only into PINNED host memory: a device-to-host copy into pageable memory returns when it is done, so the
+    // pieces would run one after the other and each would pay the bucketing passes again
+    cudaPointerAttributes pa;
+    const bool pinned = cudaPointerGetAttributes(&pa, probs) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // unregistered host memory reports an error on old drivers
+    const int chunks = (pinned && cnt >= (4u << 20)) ? 4 : 1;
     for (int c = 0; c < chunks; ++c) {
         const uint64_t b = chunks == 1 ? 0 : (uint64_t)((double)cnt * cut[c]);
         const uint64_t e = chunks == 1 ? cnt : (c + 1 == chunks ? cnt : (uint64_t)((double)cnt * cut[c + 1]));

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
             const double scale = sqrt(fin * fout);
             const double re = (2.0 * dr) / scale, im = (2.0 * di) / scale;
             const uint64_t o = it_begin + it;
+            LWB_BOUNDS(o < a.n_out);
             if (a.out_probs) {
                 const double pr_out = re * re + im * im;
                 outp[o] = pr_out;

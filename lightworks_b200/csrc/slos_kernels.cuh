@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(SLOS_THREADS, LWB_SLOS_MINB) slos_layer_kernel
             if (p + 1 < K) last_of_run = x[p + 1 < K ? p + 1 : p] != x[p];
             if (last_of_run) {
                 const IDX prank = rank - Q[p + 1];
+                LWB_BOUNDS((uint64_t)prank < a.S);  // a parent layer is never larger than its child layer
                 double2 t = a.parent[prank];
                 if (run > 1) {  // key[mode] ** 0.5 * value ; multiplying by sqrt(1) = 1.0 is exact, skip it
                     const double s = sq[run];

@@ -76,6 +76,7 @@ struct SlosUnitsArgs {
     const double* sqrt_tab;
     int write_probs;
     uint32_t max_tp;
+    uint64_t n_children, n_parents;  // layer sizes (debug bounds checks)
 };
 
 __device__ __forceinline__ double2 su_cmul_py(double2 a, double2 b) {  // CPython's complex_mul, no fma
@@ -114,6 +115,7 @@ __device__ __forceinline__ void su_trailing(uint64_t y, uint32_t c, int ell, boo
         if (i + 1 < D) last_of_run = (int)((((i + 1) < 4 ? lo : hi) >> (8 * ((i + 1) & 3))) & 0xffu) != yi;
         if (last_of_run) {
             if (!(has_ell && yi == ell)) {
+                LWB_BOUNDS(c - Q < LWB_SU_TMAX);  // inside the staged parent block (the caller checks c - Q < Tp)
                 double2 t = pb[c - Q];
                 if (run > 1) {
                     const double f = sq[run];
@@ -174,7 +176,10 @@ __device__ __forceinline__ void su_pass(const SlosUnitsArgs& a, const SlosUnit& 
         if (s < np) {
             const uint64_t off = un.sbase[s];
 #pragma unroll
-            for (int j = 0; j < NJ; ++j) buf[j] = *reinterpret_cast<const double2*>(pj[j] + off);
+            for (int j = 0; j < NJ; ++j) {
+                LWB_BOUNDS(off / 16 + c[j] < a.n_parents);
+                buf[j] = *reinterpret_cast<const double2*>(pj[j] + off);
+            }
         }
     };
     auto use = [&](const double2 (&buf)[NJ], int s) {
@@ -238,6 +243,7 @@ __device__ __forceinline__ void su_pass(const SlosUnitsArgs& a, const SlosUnit& 
         }
         if (base + j * SU_THREADS + tid < T) {
             const uint64_t rank = un.start + c[j];
+            LWB_BOUNDS(rank < a.n_children);
             if (a.write_probs)  // abs(a) ** 2 (slos.py:74); x*x + y*y differs from hypot(x, y)^2 by <= 2 ulp
                 reinterpret_cast<double*>(a.child)[rank] = __dadd_rn(__dmul_rn(acc[j].x, acc[j].x), __dmul_rn(acc[j].y, acc[j].y));
             else
@@ -453,6 +459,8 @@ int slos_units_layer(SlosUnitsState* st, cudaStream_t stream, int m, int k, cons
     a.units = pl->d_units; a.items = pl->d_items; a.lut = pl->d_lut; a.ht = pl->d_ht;
     a.m = m; a.k = k; a.parent = parent; a.child = child; a.U = U; a.in_mode = in_mode; a.sqrt_tab = sqrt_tab;
     a.write_probs = write_probs; a.max_tp = pl->max_tp;
+    a.n_children = binom(host_bin(), m + k - 1, k);
+    a.n_parents = k >= 1 ? binom(host_bin(), m + k - 2, k - 1) : 1;
     const size_t smem = (size_t)m * 16 + (size_t)pl->max_tp * 16 + (size_t)((k + 2) & ~1) * 8 + (size_t)SU_DMAX * (m + 1) * 4;
     if (smem > 200 * 1024) { *err = "slos units: parent block does not fit shared memory"; return LWB_E_LIMIT; }
     if (smem > 48 * 1024) SU_CU(cudaFuncSetAttribute(slos_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
