@@ -143,17 +143,29 @@ __device__ __forceinline__ void row_fma(T (&wr)[N], T (&wi)[N], const typename v
     }
 }
 
-// (Dynamic flips multiply the row by a +-1.0 sign with a DFMA.  Branching to the 2-operand add / subtract forms
-// for warp-uniform signs was measured SLOWER on B200 - it splits the unrolled block and ptxas schedules worse.)
+// Dynamic flips (sign known only at run time).  A DFMA with the +-1.0 sign as third register operand costs 3 issue
+// cycles on B200 (register-file bandwidth), a DADD 2.  Round 2: the row table is followed by its NEGATED copy
+// (neg_off elements further), so a flip with a run-time sign is a plain add from one of the two copies - the sign only
+// selects the address.  w + (-a) rounds exactly like fma(-1, a, w), so results are bit-identical to the DFMA form.
+// (Branching to the add / subtract forms instead was measured SLOWER in round 1: it splits the unrolled block.)
+template <int N, typename T>
+__device__ __forceinline__ void row_sgn(T (&wr)[N], T (&wi)[N], const typename vec2<T>::type* __restrict__ row, bool negative,
+                                        int neg_off) {
+    row_addsub<N, T, false>(wr, wi, row + (negative ? neg_off : 0));
+}
 
 // One chunk of 2^C Gray steps.
 //   rows   : shared-memory row table (row r starts at rows + r*N)
 //   rowidx : shared memory, N ints: rowidx[i] = (table row of matrix row i) * N
 //   q      : chunk index
 // Adds sign-corrected  sum_{t} (+-) prod_j w_j  of this chunk to (acc_re, acc_im).
-template <int N, int C, int U, typename T>
+template <int N, int C, int U, typename T, bool NEG = true>
 __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __restrict__ rows,
-                                            const int* __restrict__ rowidx, uint32_t q, T& acc_re, T& acc_im) {
+                                            const int* __restrict__ rowidx, uint32_t q, T& acc_re, T& acc_im, int neg_off) {
+    auto flip = [&](T (&wr_)[N], T (&wi_)[N], const typename vec2<T>::type* r_, bool negative) {
+        if constexpr (NEG) row_sgn<N, T>(wr_, wi_, r_, negative, neg_off);
+        else row_fma<N, T>(wr_, wi_, r_, negative ? T(-1) : T(1));
+    };
     static_assert(U <= C && C <= N - 1, "bad chunk shape");
     using V = typename vec2<T>::type;
     T wr[N], wi[N];
@@ -170,7 +182,7 @@ __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __rest
     for (int i = 0; i < N - 1; ++i) {
         const V* r = rows + lds_i(rowidx + i);
         if (i < C - 1) row_addsub<N, T, false>(wr, wi, r);  // low gray bits of an aligned chunk start are 0
-        else row_fma<N, T>(wr, wi, r, ((gr0 >> i) & 1) ? T(-1) : T(1));
+        else flip(wr, wi, r, ((gr0 >> i) & 1) != 0);
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) { wr[j] *= T(0.5); wi[j] *= T(0.5); }
@@ -204,7 +216,7 @@ __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __rest
                     // k == U-1 (middle of the block): bit U of the global index decides.  (A branch to the add/sub
                     // forms for the warp-uniform case was measured SLOWER here: it splits the unrolled block.)
                     const uint32_t hi = (U == C) ? (q & 1u) : (ob & 1u);
-                    row_fma<N, T>(wr, wi, lowrow[k], hi ? T(1) : T(-1));  // newbit = 1 ^ hi
+                    flip(wr, wi, lowrow[k], !hi);  // newbit = 1 ^ hi
                 }
             }
         }
@@ -215,7 +227,7 @@ __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __rest
             uint32_t newbit;
             if (k == C - 1) newbit = 1u ^ (q & 1u);
             else newbit = ((o1 >> (k - U)) ^ (o1 >> (k - U + 1))) & 1u;
-            row_fma<N, T>(wr, wi, rows + lds_i(rowidx + k), newbit ? T(-1) : T(1));
+            flip(wr, wi, rows + lds_i(rowidx + k), newbit != 0);
         }
     }
     const T s0 = (__popcll(gr0) & 1) ? T(-1) : T(1);
@@ -230,10 +242,14 @@ __device__ __forceinline__ void glynn_chunk(const typename vec2<T>::type* __rest
 // so the sign alternates with the step index and needs no per-chunk correction (C >= 1).
 // Used by the single-large-permanent kernel: every lane of the GPU owns an equal share of the Gray space
 // regardless of how 2^(n-1) divides by the lane count (no tail quantisation, one setup per lane).
-template <int N, int C, int U, typename T>
+template <int N, int C, int U, typename T, bool NEG = true>
 __device__ __forceinline__ void glynn_range(const typename vec2<T>::type* __restrict__ rows,
                                             const int* __restrict__ rowidx, uint64_t q_begin, uint64_t n_chunks,
-                                            T& acc_re, T& acc_im) {
+                                            T& acc_re, T& acc_im, int neg_off) {
+    auto flip = [&](T (&wr_)[N], T (&wi_)[N], const typename vec2<T>::type* r_, bool negative) {
+        if constexpr (NEG) row_sgn<N, T>(wr_, wi_, r_, negative, neg_off);
+        else row_fma<N, T>(wr_, wi_, r_, negative ? T(-1) : T(1));
+    };
     static_assert(U <= C && C <= N - 1 && C >= 1, "bad chunk shape");
     using V = typename vec2<T>::type;
     if (n_chunks == 0) return;
@@ -249,7 +265,7 @@ __device__ __forceinline__ void glynn_range(const typename vec2<T>::type* __rest
     for (int i = 0; i < N - 1; ++i) {
         const V* r = rows + lds_i(rowidx + i);
         if (i < C - 1) row_addsub<N, T, false>(wr, wi, r);
-        else row_fma<N, T>(wr, wi, r, ((gr0 >> i) & 1) ? T(-1) : T(1));
+        else flip(wr, wi, r, ((gr0 >> i) & 1) != 0);
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) { wr[j] *= T(0.5); wi[j] *= T(0.5); }
@@ -281,7 +297,7 @@ __device__ __forceinline__ void glynn_range(const typename vec2<T>::type* __rest
                         else row_addsub<N, T, false>(wr, wi, lowrow[k]);
                     } else {
                         const uint32_t hi = (U == C) ? (uint32_t)(q & 1u) : (ob & 1u);
-                        row_fma<N, T>(wr, wi, lowrow[k], hi ? T(1) : T(-1));
+                        flip(wr, wi, lowrow[k], !hi);
                     }
                 }
             }
@@ -291,7 +307,7 @@ __device__ __forceinline__ void glynn_range(const typename vec2<T>::type* __rest
                 uint32_t newbit;
                 if (k == C - 1) newbit = 1u ^ (uint32_t)(q & 1u);
                 else newbit = ((o1 >> (k - U)) ^ (o1 >> (k - U + 1))) & 1u;
-                row_fma<N, T>(wr, wi, rows + lds_i(rowidx + k), newbit ? T(-1) : T(1));
+                flip(wr, wi, rows + lds_i(rowidx + k), newbit != 0);
             }
         }
         if (c + 1 < n_chunks) {  // chunk boundary: lane-specific row
@@ -299,7 +315,7 @@ __device__ __forceinline__ void glynn_range(const typename vec2<T>::type* __rest
             const int z = __ffsll((long long)q1) - 1;
             const int k = C + z;
             const uint32_t newbit = (uint32_t)((q1 >> z) ^ (q1 >> (z + 1))) & 1u;
-            row_fma<N, T>(wr, wi, rows + lds_i(rowidx + k), newbit ? T(-1) : T(1));
+            flip(wr, wi, rows + lds_i(rowidx + k), newbit != 0);
         }
     }
     acc_re += sr;

@@ -14,7 +14,6 @@ static const K1Variant table[] = {
     LWB_K1_ENTRY(8, 1),
     LWB_K1_ENTRY(6, 1),
     LWB_K1_ENTRY(7, 1),
-    LWB_K1_ENTRY(8, 0),
     LWB_K1_ENTRY(8, 2),
 };
 const K1Variant* k1_g0_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }

@@ -6,9 +6,7 @@ namespace lwb {
 static const K1Variant table[] = {
     LWB_K1_ENTRY(9, 1),
     LWB_K1_ENTRY(10, 1),
-    LWB_K1_ENTRY(9, 0),
     LWB_K1_ENTRY(9, 2),
-    LWB_K1_ENTRY(10, 0),
     LWB_K1_ENTRY(10, 2),
     LWB_K1_ENTRY(10, 3),
 };

@@ -6,11 +6,8 @@ namespace lwb {
 static const K1Variant table[] = {
     LWB_K1_ENTRY(11, 2),
     LWB_K1_ENTRY(12, 2),
-    LWB_K1_ENTRY(11, 1),
     LWB_K1_ENTRY(11, 3),
-    LWB_K1_ENTRY(12, 1),
     LWB_K1_ENTRY(12, 3),
-    LWB_K1_ENTRY(12, 4),
 };
 const K1Variant* k1_g2_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

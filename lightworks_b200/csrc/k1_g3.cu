@@ -6,11 +6,8 @@ namespace lwb {
 static const K1Variant table[] = {
     LWB_K1_ENTRY(13, 3),
     LWB_K1_ENTRY(14, 3),
-    LWB_K1_ENTRY(13, 2),
     LWB_K1_ENTRY(13, 4),
-    LWB_K1_ENTRY(14, 2),
     LWB_K1_ENTRY(14, 4),
-    LWB_K1_ENTRY(14, 5),
 };
 const K1Variant* k1_g3_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -7,9 +7,6 @@ static const K1Variant table[] = {
     LWB_K1_ENTRY(15, 4),
     LWB_K1_ENTRY(16, 5),
     LWB_K1_ENTRY(17, 5),
-    LWB_K1_ENTRY(15, 5),
-    LWB_K1_ENTRY(16, 3),
-    LWB_K1_ENTRY(16, 4),
 };
 const K1Variant* k1_g4_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -7,9 +7,6 @@ static const K1Variant table[] = {
     LWB_K1_ENTRY(18, 5),
     LWB_K1_ENTRY(19, 5),
     LWB_K1_ENTRY(20, 5),
-    LWB_K1_ENTRY(18, 4),
-    LWB_K1_ENTRY(20, 3),
-    LWB_K1_ENTRY(20, 4),
 };
 const K1Variant* k1_g5_table(int* count) { *count = (int)(sizeof(table) / sizeof(table[0])); return table; }
 }  // namespace lwb

@@ -439,7 +439,7 @@ int k1x_basis_probs(K1xState* st, cudaStream_t stream, const uint64_t* d_bin, co
     ka.n_types = pl->n_types; ka.bucket = st->d_bucket; ka.cnt = (uint32_t)cnt; ka.probs = d_probs;
     ka.mir.n = 0;
     if (mirrors) ka.mir = *mirrors;
-    const size_t smem = (size_t)m * (n | 1) * (dtype ? 8 : 16) + (size_t)n * tb * 4;
+    const size_t smem = (size_t)2 * m * (n | 1) * (dtype ? 8 : 16) + (size_t)n * tb * 4;  // table + negated copy, slot offsets
     K1xFn fn = table[n][dtype];
     if (smem > 48 * 1024) K1X_CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const uint64_t grid = (cnt + tb - 1) / tb + (uint64_t)pl->n_types;

@@ -74,6 +74,7 @@ struct K1xArgs {
 template <int TB, typename T>
 struct K1xLane {   // what the prologue hands to the walk of one permanent
     uint32_t vs_base;  // shared-memory address of the U[:, input columns] table, row stride NP complex entries
+    uint32_t neg_bytes;  // byte distance to the NEGATED copy of the table (run-time signs select the copy: see row_sgn)
     const int* srow;   // [N][TB]: row offset (in complex entries) of slot sl for lane tid at srow[sl * TB + tid]
     int tid;
     __device__ __forceinline__ uint32_t slot_addr(int sl) const {
@@ -199,12 +200,12 @@ __device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N), T>
                         }
                     } else {  // k == U-1: bit U of the step index decides
                         const uint32_t hi = (U == C) ? par : (ob & 1u);
-                        const T sg = hi ? T(1) : T(-1);
+                        const uint32_t ra = lowaddr[k] + (hi ? 0u : ln.neg_bytes);  // sign -1: add the negated row
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
-                            const auto v = k1x_ld(lowaddr[k], j, T());
-                            wr[j] = fma(sg, v.x, wr[j]);
-                            wi[j] = fma(sg, v.y, wi[j]);
+                            const auto v = k1x_ld(ra, j, T());
+                            wr[j] += v.x;
+                            wi[j] += v.y;
                         }
                     }
                 }
@@ -213,26 +214,24 @@ __device__ __forceinline__ void k1x_static_walk(const K1xLane<k1x_threads(N), T>
                 const uint32_t o1 = ob + 1;
                 const int k = U + (__ffs(o1) - 1);
                 const uint32_t newbit = (k == C - 1) ? (1u ^ par) : (((o1 >> (k - U)) ^ (o1 >> (k - U + 1))) & 1u);
-                const T sg = newbit ? T(-1) : T(1);
-                const uint32_t ra = ln.slot_addr(d - 1 - k);
+                const uint32_t ra = ln.slot_addr(d - 1 - k) + (newbit ? ln.neg_bytes : 0u);
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
                     const auto v = k1x_ld(ra, j, T());
-                    wr[j] = fma(sg, v.x, wr[j]);
-                    wi[j] = fma(sg, v.y, wi[j]);
+                    wr[j] += v.x;
+                    wi[j] += v.y;
                 }
             }
         }
         sr = fma(st.coef, (double)cr, sr);  // chunk sums join the double accumulator
         si = fma(st.coef, (double)ci, si);
         if (t + 1 < n_steps) {  // next tuple of the bunched rows: v_slot += dir  =>  w -= dir * row
-            const T sg = st.dir > 0 ? T(-1) : T(1);
-            const uint32_t ra = ln.slot_addr(st.slot);
+            const uint32_t ra = ln.slot_addr(st.slot) + (st.dir > 0 ? ln.neg_bytes : 0u);
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 const auto v = k1x_ld(ra, j, T());
-                wr[j] = fma(sg, v.x, wr[j]);
-                wi[j] = fma(sg, v.y, wi[j]);
+                wr[j] += v.x;
+                wi[j] += v.y;
             }
         }
     }
@@ -265,8 +264,8 @@ __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
     if (blockIdx.x >= a.bstart[a.n_types]) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = N | 1;  // odd row stride (in complex entries): lanes reading different rows spread over the banks
-    V* Vs = reinterpret_cast<V*>(smem_raw);                     // [m][NP]
-    int* srow = reinterpret_cast<int*>(Vs + (size_t)a.m * NP);  // [N][TB] row offsets per slot
+    V* Vs = reinterpret_cast<V*>(smem_raw);                         // [2][m][NP]: the table and its negated copy
+    int* srow = reinterpret_cast<int*>(Vs + (size_t)2 * a.m * NP);  // [N][TB] row offsets per slot
     __shared__ int incol[N];
     __shared__ double fin_s;
     __shared__ TypeMeta tm;
@@ -311,6 +310,9 @@ __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
         v.x = (T)u.x;
         v.y = (T)u.y;
         Vs[r * NP + c] = v;
+        v.x = -v.x;
+        v.y = -v.y;
+        Vs[(m + r) * NP + c] = v;
     }
     __syncthreads();
     const uint32_t item = range[0] + tid;
@@ -336,6 +338,7 @@ __device__ __forceinline__ void k1x_block(const K1xArgs& a) {
     }
     K1xLane<TB, T> ln;
     ln.vs_base = (uint32_t)__cvta_generic_to_shared(Vs);
+    ln.neg_bytes = (uint32_t)(m * NP * sizeof(V));
     ln.srow = srow;
     ln.tid = tid;
     double sr, si;

@@ -335,20 +335,21 @@ int lwb_perm_matrices_dev(lwb_handle h, const double* d_A, uint64_t B, int n, in
     // every group of a block stages its own n x n matrix: of the compiled variants (default first) take the first
     // whose tile leaves room for two blocks per SM, unless a variant was requested explicitly
     const size_t esz = dtype == LWB_C128 ? 16 : 8;
+    const size_t nt = k1_neg(n) ? 2 : 1;
     const K1Variant* v = pick_k1(n);
     if (g_tune_logl[n] < 0) {
         const K1Variant* best = nullptr;
         for (const auto& c : g_k1) {
             if (c.n != n) continue;
-            const size_t need = (size_t)(K1_THREADS >> c.log_l) * n * n * esz;
-            if (need <= 100 * 1024) { best = &c; break; }
-            if (!best || need < (size_t)(K1_THREADS >> best->log_l) * n * n * esz) best = &c;
+            const size_t need = (size_t)(K1_THREADS >> c.log_l) * nt * n * n * esz;  // matrix (+ negated copy) per group
+            if (need <= (nt == 2 ? 160u : 100u) * 1024) { best = &c; break; }
+            if (!best || need < (size_t)(K1_THREADS >> best->log_l) * nt * n * n * esz) best = &c;
         }
         v = best;
     }
     const int gpb = K1_THREADS >> v->log_l;
-    const size_t smem = (size_t)gpb * n * n * esz;
-    if (smem > 200 * 1024) return fail(LWB_E_LIMIT, "matrix batch tile needs %zu B of shared memory", smem);
+    const size_t smem = (size_t)gpb * nt * n * n * esz;
+    if (smem > 220 * 1024) return fail(LWB_E_LIMIT, "matrix batch tile needs %zu B of shared memory", smem);
     auto fn = v->matrices[dtype];
     int resident = 0;
     CK(resident_blocks(h, fn, smem, &resident));
@@ -397,7 +398,7 @@ int lwb::launch_states(lwb_handle h, const double* d_U, int m, const uint8_t* d_
     }
     const K1Variant* v = pick_k1(n);
     const int gpb = K1_THREADS >> v->log_l;
-    const size_t smem = (size_t)m * n * (dtype == LWB_C128 ? 16 : 8) + (size_t)gpb * n * sizeof(int);
+    const size_t smem = (size_t)(k1_neg(n) ? 2 : 1) * m * n * (dtype == LWB_C128 ? 16 : 8) + (size_t)gpb * n * sizeof(int);  // rows (+ negated rows)
     auto fn = v->states[dtype];
     int resident = 0;
     CK(resident_blocks(h, fn, smem, &resident));

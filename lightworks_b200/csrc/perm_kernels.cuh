@@ -45,16 +45,20 @@ struct K1Shape {
 #ifndef LWB_F32_RESTART
 #define LWB_F32_RESTART 9
 #endif
+// The negated copy of the row table (glynn.cuh row_sgn) pays from 10 photons on: below, a permanent has so few Gray
+// steps that staging twice the shared memory per matrix costs more than the 3-cycle DFMAs it removes.
+__host__ __device__ constexpr bool k1_neg(int n) { return n >= 10; }
+
 template <int N, int C, int U, typename T>
 __device__ __forceinline__ void glynn_chunk_acc(const typename vec2<T>::type* __restrict__ rows,
-                                                const int* __restrict__ rowidx, uint32_t q, double& dr, double& di) {
+                                                const int* __restrict__ rowidx, uint32_t q, double& dr, double& di, int neg_off) {
     constexpr bool SPLIT = sizeof(T) == 4 && C > LWB_F32_RESTART;
     constexpr int R = SPLIT ? LWB_F32_RESTART : C;
     constexpr int UR = U < R ? U : R;
 #pragma unroll 1
     for (uint32_t i = 0; i < (1u << (C - R)); ++i) {
         T sr = T(0), si = T(0);
-        glynn_chunk<N, R, UR, T>(rows, rowidx, (q << (C - R)) + i, sr, si);
+        glynn_chunk<N, R, UR, T, k1_neg(N)>(rows, rowidx, (q << (C - R)) + i, sr, si, neg_off);
         dr += (double)sr;
         di += (double)si;
     }
@@ -87,8 +91,10 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
     using S = K1Shape<N, LOG_L>;
     using V = typename vec2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    V* Vs = reinterpret_cast<V*>(smem_raw);                        // [m][N]
-    int* rowidx_all = reinterpret_cast<int*>(Vs + (size_t)a.m * N);  // [GPB][N]
+    constexpr int NT = k1_neg(N) ? 2 : 1;
+    V* Vs = reinterpret_cast<V*>(smem_raw);                        // [NT][m][N]: the row table (and its negated copy)
+    int* rowidx_all = reinterpret_cast<int*>(Vs + (size_t)NT * a.m * N);  // [GPB][N]
+    const int neg_off = a.m * N;
     __shared__ int incol[N];
     __shared__ double fin_s;
 
@@ -117,6 +123,11 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
         v.x = (T)u.x;
         v.y = (T)u.y;
         Vs[e] = v;
+        if constexpr (k1_neg(N)) {
+            v.x = -v.x;
+            v.y = -v.y;
+            Vs[neg_off + e] = v;
+        }
     }
 
     const int g_in_blk = tid >> LOG_L;
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_states_kernel(PermS
     for (uint64_t it = 0; it < max_len; ++it) {
         const bool active = it < my_len;
         double dr = 0.0, di = 0.0;
-        glynn_chunk_acc<N, S::C, S::U, T>(Vs, rowidx, (uint32_t)lane_g, dr, di);
+        glynn_chunk_acc<N, S::C, S::U, T>(Vs, rowidx, (uint32_t)lane_g, dr, di, neg_off);
         dr = group_sum<double>(dr, LOG_L);
         di = group_sum<double>(di, LOG_L);
         __syncwarp();
@@ -223,13 +234,15 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_matrices_kernel(Per
     using S = K1Shape<N, LOG_L>;
     using V = typename vec2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    V* Ms_all = reinterpret_cast<V*>(smem_raw);  // [GPB][N*N]
+    V* Ms_all = reinterpret_cast<V*>(smem_raw);  // [GPB][2][N*N]: every group's matrix and its negated copy
     __shared__ int ident[N];
     const int tid = threadIdx.x;
     if (tid < N) ident[tid] = tid * N;
     const int g_in_blk = tid >> LOG_L;
     const int lane_g = tid & (S::L - 1);
-    V* Ms = Ms_all + (size_t)g_in_blk * N * N;
+    constexpr int NT = k1_neg(N) ? 2 : 1;
+    V* Ms = Ms_all + (size_t)g_in_blk * NT * N * N;
+    constexpr int neg_off = N * N;
     const uint64_t total_groups = (uint64_t)gridDim.x * S::GPB;
     const uint64_t gid = (uint64_t)blockIdx.x * S::GPB + g_in_blk;
     const uint64_t iters = (a.B + total_groups - 1) / total_groups;
@@ -246,13 +259,18 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_matrices_kernel(Per
                 v.x = (T)u.x;
                 v.y = (T)u.y;
                 Ms[e] = v;
+                if constexpr (k1_neg(N)) {
+                    v.x = -v.x;
+                    v.y = -v.y;
+                    Ms[neg_off + e] = v;
+                }
             }
         } else if (it == 0) {
-            for (int e = lane_g; e < N * N; e += S::L) { V v; v.x = T(0); v.y = T(0); Ms[e] = v; }
+            for (int e = lane_g; e < NT * N * N; e += S::L) { V v; v.x = T(0); v.y = T(0); Ms[e] = v; }
         }
         __syncwarp();
         double dr = 0.0, di = 0.0;
-        glynn_chunk_acc<N, S::C, S::U, T>(Ms, ident, (uint32_t)lane_g, dr, di);
+        glynn_chunk_acc<N, S::C, S::U, T>(Ms, ident, (uint32_t)lane_g, dr, di, neg_off);
         dr = group_sum<double>(dr, LOG_L);
         di = group_sum<double>(di, LOG_L);
         if (lane_g == 0 && active) {
@@ -285,7 +303,10 @@ template <int N, typename T>
 __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermSingleArgs a) {
     using S = K2Shape<N>;
     using V = typename vec2<T>::type;
-    __shared__ __align__(16) V Ms[N * N];
+    // the matrix and, when both fit the 48 KB of static shared memory (n <= 38 in double), its negated copy
+    constexpr bool NEG = 2 * N * N * sizeof(V) + 1024 <= 48 * 1024;
+    constexpr int neg_off = N * N;
+    __shared__ __align__(16) V Ms[(NEG ? 2 : 1) * N * N];
     __shared__ int ident[N];
     __shared__ double red[2][K1_THREADS / 32];
     const int tid = threadIdx.x;
@@ -296,6 +317,11 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermS
         v.x = (T)u.x;
         v.y = (T)u.y;
         Ms[e] = v;
+        if constexpr (NEG) {
+            v.x = -v.x;
+            v.y = -v.y;
+            Ms[neg_off + e] = v;
+        }
     }
     __syncthreads();
     double dr = 0.0, di = 0.0;
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermS
 #pragma unroll 1
         for (uint64_t done = 0; done < cnt; done += PIECE) {
             T sr = T(0), si = T(0);
-            glynn_range<N, S::C, S::U, T>(Ms, ident, b + done, (cnt - done < PIECE) ? cnt - done : PIECE, sr, si);
+            glynn_range<N, S::C, S::U, T, NEG>(Ms, ident, b + done, (cnt - done < PIECE) ? cnt - done : PIECE, sr, si, neg_off);
             dr += (double)sr;
             di += (double)si;
         }
