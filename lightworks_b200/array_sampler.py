@@ -323,13 +323,18 @@ def _merge_first_seen(rows: np.ndarray, weights: np.ndarray):
     added sequentially in input order (np.bincount accumulates in index order)."""
     if len(rows) == 0:
         return rows, weights
-    uniq, first, inv = np.unique(rows, axis=0, return_index=True, return_inverse=True)
+    rows = np.ascontiguousarray(rows)
+    if rows.dtype != np.uint8 and rows.size and rows.max() < 256 and rows.min() >= 0:
+        rows = rows.astype(np.uint8)
+    # equal rows are found by comparing them as byte strings (one memcmp per comparison, not a lexicographic row sort)
+    as_bytes = rows.view(np.dtype((np.void, rows.dtype.itemsize * rows.shape[1]))).reshape(-1)
+    _, first, inv = np.unique(as_bytes, return_index=True, return_inverse=True)
     inv = inv.reshape(-1)
     order = np.argsort(first, kind="stable")
-    pos = np.empty(len(uniq), dtype=np.int64)
-    pos[order] = np.arange(len(uniq))
-    sums = np.bincount(pos[inv], weights=weights, minlength=len(uniq))
-    return uniq[order], sums
+    pos = np.empty(len(first), dtype=np.int64)
+    pos[order] = np.arange(len(first))
+    sums = np.bincount(pos[inv], weights=weights, minlength=len(first))
+    return rows[first[order]], sums
 
 
 def distribution_arrays(backend, circuit, inputs: dict, threshold: float):

@@ -696,6 +696,10 @@ extern "C" int lwb_dists_from_circuit(lwb_handle h, lwb_comm comm, const double*
         CU(cudaMemcpyAsync(w->bU.p, U_full, (size_t)m_tot * m_tot * 16, cudaMemcpyHostToDevice, w->stream));
         if (g > 0) CK(ensure(w, w->bRes, kmax_size * 8));
     }
+    if (nw > 1) {  // other devices' streams will write into slots that may be recycled buffers: drain h's pending readers
+        CU(cudaSetDevice(h->device));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     int made = 0, rc = 0;
     for (int k = 0; k < count && rc == 0; ++k) {
         const uint8_t* ins = in_states + (size_t)k * n_modes;

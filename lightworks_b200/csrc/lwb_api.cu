@@ -160,6 +160,7 @@ int lwb_destroy(lwb_handle h) {
     slos_units_destroy(h->slos_units);
     for (auto& d : h->dists)
         if (d.p) cudaFree(d.p);
+    for (auto& kv : h->dist_pool) cudaFree(kv.second);
     if (h->d_bin) cudaFree(h->d_bin);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -170,6 +171,7 @@ int lwb_destroy(lwb_handle h) {
 
 int lwb_set_stream(lwb_handle h, void* s, int use_own) {
     if (!h) return fail(LWB_E_ARG, "null handle");
+    if (!h->dist_pool.empty()) CU(cudaStreamSynchronize(h->stream));  // parked buffers are ordered on the OLD stream
     h->stream = use_own ? h->own_stream : (cudaStream_t)s;  // s == NULL is the legacy default stream
     return 0;
 }
@@ -1170,8 +1172,25 @@ static int new_slot(lwb_handle h, int n_modes, int kmin, int kmax, int* slot) {
     CK(keyspace_check(n_modes, kmax));
     lwb_context::DistSlot d;
     d.n_modes = n_modes; d.kmin = kmin; d.kmax = kmax; d.size = keyspace_off(n_modes, kmax + 1);
-    cudaError_t e = cudaMalloc((void**)&d.p, d.size * 8);
-    if (e != cudaSuccess) return fail(LWB_E_NOMEM, "cudaMalloc(%llu): %s", (unsigned long long)(d.size * 8), cudaGetErrorString(e));
+    for (size_t i = 0; i < h->dist_pool.size(); ++i)  // a parked buffer of exactly this size
+        if (h->dist_pool[i].first == d.size) {
+            d.p = h->dist_pool[i].second;
+            h->dist_pool_bytes -= d.size * 8;
+            h->dist_pool[i] = h->dist_pool.back();
+            h->dist_pool.pop_back();
+            break;
+        }
+    if (!d.p) {
+        cudaError_t e = cudaMalloc((void**)&d.p, d.size * 8);
+        if (e != cudaSuccess && !h->dist_pool.empty()) {  // out of memory with buffers parked: release them and retry
+            cudaGetLastError();
+            for (auto& kv : h->dist_pool) cudaFree(kv.second);
+            h->dist_pool.clear();
+            h->dist_pool_bytes = 0;
+            e = cudaMalloc((void**)&d.p, d.size * 8);
+        }
+        if (e != cudaSuccess) return fail(LWB_E_NOMEM, "cudaMalloc(%llu): %s", (unsigned long long)(d.size * 8), cudaGetErrorString(e));
+    }
     for (size_t i = 0; i < h->dists.size(); ++i)
         if (!h->dists[i].p) { h->dists[i] = d; *slot = (int)i; return 0; }
     h->dists.push_back(d);
@@ -1334,8 +1353,14 @@ int lwb_dist_free(lwb_handle h, int slot) {
     lwb_context::DistSlot* d = nullptr;
     CK(get_slot(h, slot, &d));
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaFree(d->p));
+    // park the buffer (up to 4 GiB in total): its next user is enqueued on the same stream, after every pending reader
+    if (h->dist_pool_bytes + d->size * 8 <= (4ull << 30) && h->dist_pool.size() < 4096) {
+        h->dist_pool.push_back({d->size, d->p});
+        h->dist_pool_bytes += d->size * 8;
+    } else {
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaFree(d->p));
+    }
     *d = lwb_context::DistSlot();
     return 0;
 }

@@ -57,6 +57,10 @@ struct lwb_context {
         uint64_t size = 0;
     };
     std::vector<DistSlot> dists;
+    // freed distribution buffers by size in doubles: lwb_dist_free parks them here instead of cudaFree (which
+    // synchronises the device) and new slots reuse them - everything is ordered on the handle's stream
+    std::vector<std::pair<uint64_t, double*>> dist_pool;
+    uint64_t dist_pool_bytes = 0;
     std::mutex mu;
 };
 
