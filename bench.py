@@ -534,8 +534,9 @@ def main() -> int:  # noqa: PLR0915
                 line["second_headline"] = {
                     "metric": "output-state probabilities/sec (SLOS backend: complex128 state-vector evolution, full distribution)",
                     "value": sl["probabilities_per_s"], "unit": UNIT, "ms_per_step": sl["ms"], "roofline": sl["roofline"],
-                    "kernel": "slos_units_kernel (K3u: prefix units, coalesced parent streams, parent block in shared memory) x 10 layers",
-                    "gather_kernel_ms": sl.get("gather_kernel_ms")}
+                    "kernel": "slos_units4_kernel (K3r: prefix units, coalesced parent streams, parent block in shared memory, "
+                              "host-built records instead of index arithmetic) x 10 layers",
+                    "gather_kernel_ms": sl.get("gather_kernel_ms"), "unit_kernel_ms": sl.get("unit_kernel_ms")}
     if rank == 0:
         emit(line)
     if world > 1:
@@ -577,15 +578,19 @@ def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
     with torch.cuda.stream(stream):
         d_p = torch.empty(S, dtype=torch.float64, device="cuda")
     ms = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1), reps=5)
-    _lib.set_option("slos_units", 0)  # the round-1 gather-form kernel beside it
-    try:
+    ms_gather = ms_units = None
+    try:  # beside it: the round-1 gather-form kernel and the index-deriving unit kernel (same results up to rounding)
+        _lib.set_option("slos_units", 0)
         ms_gather = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1))
-    finally:
         _lib.set_option("slos_units", 1)
+        ms_units = t_ms(lambda: ctx.slos_basis_probs_dev(d_U, M, ins, d_p, order=1))
+    finally:
+        _lib.set_option("slos_units", 4)
     # algorithmic bytes: every layer reads its parent once and writes itself once (the last layer
     # writes 8-byte probabilities)
     slos_bytes = sum(16 * (comb(M + k - 2, k - 1) + comb(M + k - 1, k)) for k in range(1, N_PH + 1))
     out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms, "gather_kernel_ms": ms_gather,
+                      "unit_kernel_ms": ms_units,
                       "roofline": {"bound": "hbm", "achieved": slos_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                                    "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes},
                       "gather_traffic": {"bytes": 16 * M * sum(comb(M + k - 2, k - 1) for k in range(1, N_PH + 1)),

@@ -58,8 +58,11 @@ int lwb_set_tuning(int n, int log_l);
 /* Process-wide options.  "multiplicity_aware" (default 1): full-basis probability ranges use the
  * multiplicity-aware Glynn walk (prod(s_i+1)/2 terms for an output with occupations s_i) instead of
  * expanding repeated rows into 2^(n-1) terms; 0 forces the plain expanded-row kernel.
- * "slos_units" (default 1): SLOS layers run the prefix-unit kernel (coalesced parent streams + shared-memory parent
- * blocks, csrc/slos_units.cu); 0 forces the gather-form kernel (csrc/slos_kernels.cuh).
+ * "slos_units" (default 4): which kernel runs a SLOS layer (csrc/slos_units.cu).  4: record kernel - prefix units,
+ * coalesced parent streams, parent blocks in shared memory, host-built records instead of index arithmetic, terms
+ * accumulated with FMAs (rounding differs from the other two by ~1e-16 relative).  1: unit kernel - same units,
+ * indices derived per child, rounds exactly like the gather kernel.  0: gather-form kernel (csrc/slos_kernels.cuh),
+ * which rounds like the reference's Python complex arithmetic.
  * "source_string_keys" (default 0, test hook): lwb_source_statistics keys its classes by strings even when the
  * packed 62-bit form fits. */
 int lwb_set_option(const char* name, int value);

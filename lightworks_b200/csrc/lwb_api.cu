@@ -66,7 +66,7 @@ static std::vector<K1Variant> g_k1;
 static const K2Variant* g_k2[LWB_K2_MAX_N + 1];
 static int g_tune_logl[LWB_K1_MAX_N + 1];
 static int g_multiplicity_aware = 1;  // lwb_set_option("multiplicity_aware", 0/1)
-static int g_slos_units = 1;          // lwb_set_option("slos_units", 0/1): K3u prefix-unit kernel vs K3 gather kernel
+static int g_slos_units = 4;          // lwb_set_option("slos_units", v): 0 gather kernel (K3), 1 unit kernel (K3u), 4 record kernel (K3r)
 static std::once_flag g_tables_once;
 
 static void load_tables() {
@@ -210,7 +210,7 @@ int lwb_set_tuning(int n, int log_l) {
 int lwb_set_option(const char* name, int value) {
     if (!name) return fail(LWB_E_ARG, "null option name");
     if (!strcmp(name, "multiplicity_aware")) { g_multiplicity_aware = value ? 1 : 0; return 0; }
-    if (!strcmp(name, "slos_units")) { g_slos_units = value ? 1 : 0; return 0; }
+    if (!strcmp(name, "slos_units")) { g_slos_units = value < 0 ? 0 : (int)value; return 0; }
     if (!strcmp(name, "source_string_keys")) { lwb::g_source_string_keys = value ? 1 : 0; return 0; }
     return fail(LWB_E_ARG, "unknown option %s", name);
 }
@@ -735,7 +735,7 @@ static int launch_slos_layer(lwb_handle h, const SlosLayerArgs& a) {
     if (g_slos_units && slos_units_supported(a.m, a.k)) {
         std::string err;
         const int rc = slos_units_layer(h->slos_units, h->stream, a.m, a.k, a.parent, a.child, a.U, a.in_mode, a.sqrt_tab,
-                                        a.write_probs, &h->launches, &err);
+                                        a.write_probs, &h->launches, &err, g_slos_units >= 4 ? 4 : 3);
         if (rc == 0) return 0;
         if (rc != LWB_E_LIMIT) return fail(rc, "%s", err.c_str());  // LWB_E_LIMIT: shape outside K3u, use the gather kernel
     }

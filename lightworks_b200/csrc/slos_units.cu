@@ -27,6 +27,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "fock.cuh"
@@ -44,7 +45,14 @@ constexpr int SU_NPMAX = 16;      // distinct prefix modes per unit
 #ifndef LWB_SU_MINB
 #define LWB_SU_MINB 3
 #endif
-constexpr uint32_t SU_TMAX = LWB_SU_TMAX;   // children per unit
+constexpr uint32_t SU_TMAX = LWB_SU_TMAX;   // children per unit (large layers)
+#ifndef LWB_SU_TMAX_SMALL
+#define LWB_SU_TMAX_SMALL 4096
+#endif
+// Layers below this many children use smaller units: more CTAs, smaller parent blocks (measured: 16 modes / 8 photons
+// 0.117 -> 0.091 ms), while the largest layers prefer long units (24 modes / 10 photons: 1.97 vs 2.25 ms).
+constexpr uint64_t SU_SMALL_LAYER = 16u << 20;
+static uint32_t unit_tmax(uint64_t children) { return children < SU_SMALL_LAYER ? (uint32_t)LWB_SU_TMAX_SMALL : SU_TMAX; }
 constexpr uint32_t SU_ITEM = 4096;   // a CTA takes consecutive units until it holds this many children ...
 constexpr uint32_t SU_ITEM_MIN = 256;  // ... fewer on small layers, so that every SM gets several CTAs
 static uint32_t item_size(uint64_t children) {
@@ -58,6 +66,8 @@ struct SlosUnit {
     uint64_t sbase[SU_NPMAX];   // stream s: parent(c) = parent[sbase[s] / 16 + c]: BYTE offset of (pend - T)
     uint32_t T, Tp;             // children; amplitudes of B(P)
     uint32_t lut;               // trailing modes of child c = lut_table[lut + c]
+    uint32_t rbase;             // record kernel: child c uses record rbase + c (= rec_end(d) - T + c)
+    uint32_t pad0;
     uint8_t d, ell, np, has_ell;  // trailing photons; last prefix mode (0 if none); distinct prefix modes; l in prefix?
     uint8_t pm[SU_NPMAX];       // distinct prefix modes, ascending
     uint8_t pmult[SU_NPMAX];    // their multiplicities in the prefix
@@ -287,6 +297,194 @@ __global__ void __launch_bounds__(SU_THREADS, LWB_SU_MINB) slos_units_kernel(Slo
     }
 }
 
+// ================================================================================================================
+// K3u record kernel (option "slos_units" = 4): the same units, but no child derives an index or a multiplicity.
+// Every trailing part (d <= 8 photons over the free modes) has a host-built RECORD of one 32-bit word per run of equal
+// modes: the position of the parent "trailing part minus one photon of the run", counted from the END of the parent
+// block B(P), and the byte offset of the weight w[mode][run length] in shared memory, where
+// w[mode][mult] = U[mode, in_mode] * sqrt(mult) and w[.][0] = 0.  Records are "counted from the end", hence shared by
+// every unit with the same d whatever its first free mode l: the child c of a unit with T children uses record
+// rec_end(d) - T + c.  Unused words of a record point at w[0][0] = 0 and at a valid parent, so the trailing loop has no
+// per-lane branch.  The prefix modes are the end-aligned global streams of the unit kernel above; a thread handles
+// two children 256 apart so that one stream address and one weight serve both.  The only data-dependent step left is
+// the run of l: trailing photons in l (the first run of the record, when its mode is l) join the last prefix stream.
+// A term is parent * w, products and sums rounded one by one as in the gather kernel and in the same order, so the
+// amplitudes of collision-free paths are bit-identical to it; where a multiplicity > 1 occurs, sqrt(mult) is applied
+// to the weight instead of the parent, which changes the rounding (~1e-16 relative), not the value.
+constexpr int SU_WMAX = 2048;     // entries of w: byte offsets fit 16 bits
+constexpr uint32_t SU_NEVER = 0x80000000u;
+#ifndef LWB_SU4_J
+#define LWB_SU4_J 2
+#endif
+#ifndef LWB_SU4_PF
+#define LWB_SU4_PF 2
+#endif
+constexpr int SU4_J = LWB_SU4_J;    // children per thread and pass, SU_THREADS apart
+constexpr int SU4_PF = LWB_SU4_PF;  // prefix streams loaded ahead
+#ifndef LWB_SU4_MINB
+#define LWB_SU4_MINB LWB_SU_MINB
+#endif
+
+struct SuTables {
+    const uint4* rec_a;     // words 0-3 of every record: bits 0-15 parent position from the end (1 = last), 16-31 weight offset
+    const uint4* rec_b;     // words 4-7 (classes with d > 4)
+};
+
+// acc += v * w with every product and sum rounded separately, like the reference's complex arithmetic: two terms that
+// cancel by symmetry (Hong-Ou-Mandel: the reference's own tests ask for an exact 0) then cancel exactly, which a fused
+// multiply-add chain does not do.
+__device__ __forceinline__ void su_add_term(double2& acc, const double2 v, const double2 w) {
+    const double2 t = su_cmul_py(v, w);
+    acc.x = __dadd_rn(acc.x, t.x);
+    acc.y = __dadd_rn(acc.y, t.y);
+}
+
+// J children per thread (c0, c0 + 256, ...) of the unit `un`; children past T - 1 recompute the last one, store nothing
+template <int J>
+__device__ __forceinline__ void su4_children(const SlosUnitsArgs& a, const SuTables& tb, const SlosUnit& un, uint32_t c0,
+                                             const char* wbase, const char* pbase, const uint64_t* sptr, const uint32_t* pw,
+                                             uint32_t ell_w16, uint32_t k1_16) {
+    const uint32_t T = un.T, be = un.Tp * 16u;
+    const int d = un.d, np = un.np;
+    uint32_t cj[J];
+    uint4 ra[J], rb[J];
+    double2 acc[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        cj[j] = min(c0 + j * SU_THREADS, T - 1);
+        ra[j] = __ldg(tb.rec_a + un.rbase + cj[j]);
+        acc[j] = make_double2(0.0, 0.0);
+    }
+    // ---- prefix modes: end-aligned global streams, SU4_PF loads ahead ----
+    double2 buf[SU4_PF][J];
+    uint32_t dj[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) dj[j] = (cj[j] - c0) * 16u;
+    auto load = [&](double2 (&bf)[J], int s_) {
+        if (s_ < np) {
+            const char* p = reinterpret_cast<const char*>(sptr[s_]) + (uint64_t)c0 * 16u;
+#pragma unroll
+            for (int j = 0; j < J; ++j) bf[j] = *reinterpret_cast<const double2*>(p + dj[j]);
+        }
+    };
+#pragma unroll
+    for (int i = 0; i < SU4_PF; ++i) load(buf[i], i);
+    // the run of l: a first run of the record sitting in l joins the last prefix stream
+    uint32_t lead[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        const uint32_t t = (ra[j].x >> 16) - ell_w16;     // (run length) * 16 when the first run's mode is l
+        const bool merged = t < k1_16;
+        lead[j] = merged ? t : 0u;
+        if (merged) ra[j].x &= 0xffffu;                   // ... and then that run has no term of its own
+    }
+    auto use = [&](const double2 (&bf)[J], int s_) {
+        if (s_ < np) {
+            const uint32_t wo = pw[s_];
+            if (s_ == np - 1) {
+#pragma unroll
+                for (int j = 0; j < J; ++j) su_add_term(acc[j], bf[j], *reinterpret_cast<const double2*>(wbase + wo + lead[j]));
+            } else {
+                const double2 w = *reinterpret_cast<const double2*>(wbase + wo);
+#pragma unroll
+                for (int j = 0; j < J; ++j) su_add_term(acc[j], bf[j], w);
+            }
+        }
+    };
+    for (int s_ = 0; s_ < np; s_ += SU4_PF) {
+#pragma unroll
+        for (int i = 0; i < SU4_PF; ++i) {
+            use(buf[i], s_ + i);
+            load(buf[i], s_ + i + SU4_PF);
+        }
+    }
+    // ---- trailing runs: parents in the staged block, positions and weights from the record ----
+    auto term = [&](double2& ac, uint32_t word) {
+        LWB_BOUNDS((word & 0xffffu) >= 1 && (word & 0xffffu) * 16u <= be);
+        su_add_term(ac, *reinterpret_cast<const double2*>(pbase + (be - (word & 0xffffu) * 16u)),
+                    *reinterpret_cast<const double2*>(wbase + (word >> 16)));
+    };
+    if (d > 4) {  // second half of the records: in flight while the first half is used
+#pragma unroll
+        for (int j = 0; j < J; ++j) rb[j] = __ldg(tb.rec_b + un.rbase + cj[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        term(acc[j], ra[j].x);
+        if (d > 1) term(acc[j], ra[j].y);
+        if (d > 2) term(acc[j], ra[j].z);
+        if (d > 3) term(acc[j], ra[j].w);
+    }
+    if (d > 4) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            term(acc[j], rb[j].x);
+            if (d > 5) term(acc[j], rb[j].y);
+            if (d > 6) term(acc[j], rb[j].z);
+            if (d > 7) term(acc[j], rb[j].w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+        if (c0 + j * SU_THREADS >= T) break;
+        const uint64_t rank = un.start + cj[j];
+        LWB_BOUNDS(rank < a.n_children);
+        if (a.write_probs)
+            reinterpret_cast<double*>(a.child)[rank] = __dadd_rn(__dmul_rn(acc[j].x, acc[j].x), __dmul_rn(acc[j].y, acc[j].y));
+        else
+            reinterpret_cast<double2*>(a.child)[rank] = acc[j];
+    }
+}
+
+__global__ void __launch_bounds__(SU_THREADS, LWB_SU4_MINB) slos_units4_kernel(SlosUnitsArgs a, SuTables tb) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int m = a.m, k1 = a.k + 1;
+    double2* wtab = reinterpret_cast<double2*>(smem_raw);                 // [m][k + 1]
+    double2* pb = wtab + m * k1;                                          // [max_tp] parent block
+    __shared__ __align__(16) SlosUnit un2[2];
+    __shared__ uint64_t sptr[SU_NPMAX];                                   // prefix stream s: address of its first amplitude
+    __shared__ uint32_t pw[SU_NPMAX];                                     // ... and byte offset of its weight in wtab
+    const int tid = threadIdx.x;
+    for (int i = tid; i < m * k1; i += SU_THREADS) {
+        const int mode = i / k1, mult = i - mode * k1;
+        const double2 u = a.U[(size_t)mode * m + a.in_mode];
+        const double f = a.sqrt_tab[mult];
+        wtab[i] = mult ? make_double2(__dmul_rn(u.x, f), __dmul_rn(u.y, f)) : make_double2(0.0, 0.0);
+    }
+    const uint2 item = a.items[blockIdx.x];
+    constexpr int UW = (int)(sizeof(SlosUnit) / 4);
+    if (tid < UW) su_cp_async4(reinterpret_cast<uint32_t*>(&un2[0]) + tid, reinterpret_cast<const uint32_t*>(a.units + item.x) + tid);
+    int cur = 0;
+    const char* wbase = reinterpret_cast<const char*>(wtab);
+    const char* pbase = reinterpret_cast<const char*>(pb);
+    const uint32_t k1_16 = (uint32_t)k1 * 16u;
+    for (uint32_t u = item.x; u < item.y; ++u, cur ^= 1) {
+        su_cp_async_wait();
+        __syncthreads();  // descriptor `cur` has arrived; everybody is done with the previous unit's `pb`, `sptr`, `pw`
+        const SlosUnit& un = un2[cur];
+        const uint32_t T = un.T, Tp = un.Tp;
+        const double2* pblk = a.parent + un.pblock;
+        for (uint32_t i = tid; i < Tp; i += SU_THREADS) su_cp_async16(pb + i, pblk + i);
+        if (tid < un.np) {
+            pw[tid] = (uint32_t)(un.pm[tid] * k1 + un.pmult[tid]) * 16u;
+            sptr[tid] = reinterpret_cast<uint64_t>(a.parent) + un.sbase[tid];
+        }
+        // weight offset of (l, 0): a record whose first run is in l merges with the last prefix stream
+        const uint32_t ell_w16 = un.has_ell ? (uint32_t)un.ell * k1_16 : SU_NEVER;
+        su_cp_async_wait();
+        __syncthreads();  // parent block, `sptr` and `pw` staged
+        if (u + 1 < item.y && tid < UW)
+            su_cp_async4(reinterpret_cast<uint32_t*>(&un2[cur ^ 1]) + tid, reinterpret_cast<const uint32_t*>(a.units + u + 1) + tid);
+        for (uint32_t c0 = tid; c0 < T; c0 += SU4_J * SU_THREADS) {
+            // warp-uniform choice: some lane of this warp has a second child, or none has
+            if (SU4_J > 1 && (c0 & ~31u) + SU_THREADS < T)
+                su4_children<SU4_J>(a, tb, un, c0, wbase, pbase, sptr, pw, ell_w16, k1_16);
+            else
+                su4_children<1>(a, tb, un, c0, wbase, pbase, sptr, pw, ell_w16, k1_16);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host plan: units, items and tables of one layer (m modes, k photons in the child layer)
 struct SlosLayerPlan {
@@ -296,6 +494,10 @@ struct SlosLayerPlan {
     uint2* d_items = nullptr;
     uint64_t* d_lut = nullptr;
     uint32_t* d_ht = nullptr;
+    uint4* d_rec_a = nullptr;    // record kernel; has_tables = false when not representable (the unit kernel serves the layer)
+    uint4* d_rec_b = nullptr;
+    SuTables tables;
+    bool has_tables = false;
 };
 
 struct SlosUnitsState {
@@ -310,6 +512,8 @@ void slos_units_destroy(SlosUnitsState* st) {
         cudaFree(kv.second.d_items);
         cudaFree(kv.second.d_lut);
         cudaFree(kv.second.d_ht);
+        cudaFree(kv.second.d_rec_a);
+        cudaFree(kv.second.d_rec_b);
     }
     delete st;
 }
@@ -322,6 +526,7 @@ uint64_t simplex(const uint64_t* bin, int n_free, int d) { return binom(bin, n_f
 struct Builder {
     const uint64_t* bin;
     int m, k;
+    uint32_t tmax = SU_TMAX;
     std::vector<SlosUnit> units;
     int nf_max[SU_DMAX + 1];   // per d: largest n_free among the units
     int x[LWB_MAX_PHOTONS + 2];
@@ -371,13 +576,132 @@ struct Builder {
         if (!ok) return;
         const int d = k - depth, ell = depth ? x[depth - 1] : 0;
         const uint64_t t = simplex(bin, m - ell, d);
-        if (d <= SU_DMAX && t <= SU_TMAX && d >= 1) { emit(depth); return; }
+        if (d <= SU_DMAX && t <= tmax && d >= 1) { emit(depth); return; }
         for (int v = ell; v < m; ++v) {
             x[depth] = v;
             walk(depth + 1);
         }
     }
 };
+
+// Records of the record kernel (see slos_units4_kernel): per d the d-simplex over the modes [m - nf_max[d], m) in lex
+// order, one record each.  Sets rbase of every unit.
+struct SuHostTables {
+    std::vector<uint4> rec_a, rec_b;
+    uint32_t rec_off[SU_DMAX + 1] = {0}, rec_size[SU_DMAX + 1] = {0};
+};
+
+bool build_tables(const uint64_t* bin, int m, int k, Builder& b, SuHostTables& t) {
+    if (m * (k + 1) > SU_WMAX) return false;
+    const int k1 = k + 1;
+    for (int d = 1; d <= SU_DMAX; ++d) {
+        if (!b.nf_max[d]) continue;
+        const int nf = b.nf_max[d], lo = m - nf;
+        const uint64_t size = simplex(bin, nf, d), psize = simplex(bin, nf, d - 1);
+        if (size > 0x7fffffffull || psize > 0xffff) return false;
+        t.rec_off[d] = (uint32_t)t.rec_a.size();
+        t.rec_size[d] = (uint32_t)size;
+        int y[SU_DMAX];
+        for (int i = 0; i < d; ++i) y[i] = lo;
+        for (uint64_t c = 0; c < size; ++c) {
+            uint32_t w[SU_DMAX];
+            for (int q = 0; q < SU_DMAX; ++q) w[q] = 1;  // unused: position 1 from the end (valid), weight w[0][0] = 0
+            int n_runs = 0;
+            for (int q = 0; q < d;) {
+                int j = q;
+                while (j < d && y[j] == y[q]) ++j;
+                int z[SU_DMAX], n = 0;
+                for (int i = 0; i < d; ++i)
+                    if (i != q) z[n++] = y[i] - lo;   // the trailing part minus one photon of this run
+                const uint64_t r = d > 1 ? lex_rank(bin, z, d - 1, nf) : 0;
+                const uint32_t pe = (uint32_t)(psize - r);  // counted from the end, the parent itself included
+                const uint32_t w16 = (uint32_t)(y[q] * k1 + (j - q)) * 16u;
+                w[n_runs++] = pe | (w16 << 16);
+                q = j;
+            }
+            t.rec_a.push_back(make_uint4(w[0], w[1], w[2], w[3]));
+            t.rec_b.push_back(make_uint4(w[4], w[5], w[6], w[7]));
+            for (int i = d - 1; i >= 0; --i)  // lex successor
+                if (y[i] < m - 1) {
+                    const int v = y[i] + 1;
+                    for (int q = i; q < d; ++q) y[q] = v;
+                    break;
+                }
+        }
+    }
+    for (SlosUnit& un : b.units) {
+        if (un.T > t.rec_size[un.d]) return false;
+        un.rbase = t.rec_off[un.d] + t.rec_size[un.d] - un.T;
+    }
+    return true;
+}
+
+// Replays slos_units4_kernel's index arithmetic for one unit on the host and compares every parent position it would
+// read with the exact lex rank of the child minus that photon (and every weight offset with the true multiplicity).
+int check_unit_v4(const uint64_t* bin, int m, int k, const SlosUnit& un, const SuHostTables& tb) {
+    const int d = un.d, np = un.np, k1 = k + 1;
+    int x[LWB_MAX_PHOTONS + 2], depth = 0;
+    for (int s = 0; s < np; ++s)
+        for (int q = 0; q < un.pmult[s]; ++q) x[depth++] = un.pm[s];
+    if (depth + d != k) return LWB_E_ARG;
+    if ((un.has_ell != 0) != (np > 0)) return LWB_E_ARG;   // the kernel merges into the LAST prefix stream
+    if (np > 0 && un.pm[np - 1] != un.ell) return LWB_E_ARG;
+    const uint32_t T = un.T, Tp = un.Tp, k1_16 = (uint32_t)k1 * 16u;
+    const uint32_t ell_w16 = un.has_ell ? (uint32_t)un.ell * k1_16 : SU_NEVER;
+    if ((size_t)un.rbase + T > tb.rec_a.size()) return LWB_E_ARG;
+    for (uint32_t c = 0; c < T; ++c) {
+        const uint4 ra = tb.rec_a[un.rbase + c], rb = tb.rec_b[un.rbase + c];
+        uint32_t word[SU_DMAX] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+        int tq = 0;
+        for (int q = 0; q < SU_DMAX; ++q) {  // the trailing part spelled by the runs of the record
+            const uint32_t w16 = word[q] >> 16;
+            if (w16 % 16) return LWB_E_ARG;
+            const int wi = (int)(w16 / 16);
+            if (!wi) continue;
+            if (q >= d) return LWB_E_ARG;     // the kernel reads d words only
+            for (int r = 0; r < wi % k1; ++r) {
+                if (tq >= d) return LWB_E_ARG;
+                x[depth + tq++] = wi / k1;
+            }
+        }
+        if (tq != d) return LWB_E_ARG;
+        for (int i = 1; i < k; ++i)
+            if (x[i] < x[i - 1] || x[i] >= m) return LWB_E_ARG;
+        if (lex_rank(bin, x, k, m) != un.start + c) return LWB_E_ARG;
+        const uint32_t t = (word[0] >> 16) - ell_w16;
+        const bool merged = t < k1_16;
+        const uint32_t lead = merged ? t : 0u;
+        if (merged) word[0] &= 0xffffu;
+        // every (weight, parent position) the kernel would use, in its order
+        int seen_modes[LWB_MAX_PHOTONS + 2] = {0}, n_seen = 0;
+        auto verify = [&](uint32_t w16, uint64_t parent_rank) -> bool {
+            const int mode = (int)(w16 / 16) / k1, mult = (int)(w16 / 16) % k1;
+            int true_mult = 0, at = -1;
+            for (int i = 0; i < k; ++i)
+                if (x[i] == mode) { ++true_mult; at = i; }
+            if (true_mult != mult || at < 0) return false;
+            if (n_seen && seen_modes[n_seen - 1] >= mode) return false;  // ascending, each mode once
+            seen_modes[n_seen++] = mode;
+            int y[LWB_MAX_PHOTONS + 2], n = 0;
+            for (int i = 0; i < k; ++i)
+                if (i != at) y[n++] = x[i];
+            return lex_rank(bin, y, k - 1, m) == parent_rank;
+        };
+        for (int s = 0; s < np; ++s) {
+            const uint32_t w16 = (uint32_t)(un.pm[s] * k1 + un.pmult[s]) * 16u + (s == np - 1 ? lead : 0u);
+            if (un.sbase[s] % 16 || !verify(w16, un.sbase[s] / 16 + c)) return LWB_E_ARG;
+        }
+        for (int q = 0; q < d; ++q) {
+            const uint32_t pe = word[q] & 0xffffu, w16 = word[q] >> 16;
+            if (pe == 0 || pe > Tp) return LWB_E_ARG;  // read even for a zero weight
+            if (w16 && !verify(w16, un.pblock + Tp - pe)) return LWB_E_ARG;
+        }
+        int distinct = 0;
+        for (int i = 0; i < k; ++i) distinct += i == 0 || x[i] != x[i - 1];
+        if (n_seen != distinct) return LWB_E_ARG;  // no mode of the child was skipped
+    }
+    return 0;
+}
 }  // namespace
 
 static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std::string* err) {
@@ -386,7 +710,7 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
     if (it != st->plans.end()) { *out = &it->second; return 0; }
     const uint64_t* bin = host_bin();
     Builder b;
-    b.bin = bin; b.m = m; b.k = k;
+    b.bin = bin; b.m = m; b.k = k; b.tmax = unit_tmax(binom(bin, m + k - 1, k));
     for (int d = 0; d <= SU_DMAX; ++d) b.nf_max[d] = 0;
     b.walk(0);
     if (!b.ok || b.units.empty() || b.units.size() >= (1ull << 31)) { *err = "slos units: plan not representable"; return LWB_E_LIMIT; }
@@ -431,6 +755,9 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
         for (int v = 0; v <= m; ++v) ht[(size_t)r * (m + 1) + v] = (uint32_t)binom(bin, m - v + r - 1, r + 1);
     pl.n_units = (uint32_t)b.units.size();
     pl.n_items = (uint32_t)items.size();
+    SuHostTables ht4;   // sub-unit kernel: tables and the units' hoff (before the units are uploaded)
+    memset(&pl.tables, 0, sizeof pl.tables);
+    const bool has4 = build_tables(bin, m, k, b, ht4);
 #define SU_CU(call)                                                                   \
     do {                                                                              \
         cudaError_t e_ = (call);                                                      \
@@ -444,6 +771,16 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
     SU_CU(cudaMemcpy(pl.d_items, items.data(), items.size() * sizeof(uint2), cudaMemcpyHostToDevice));
     SU_CU(cudaMemcpy(pl.d_lut, lut.data(), lut.size() * 8, cudaMemcpyHostToDevice));
     SU_CU(cudaMemcpy(pl.d_ht, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice));
+    if (has4) {
+        const size_t nrec = std::max<size_t>(ht4.rec_a.size(), 1);
+        SU_CU(cudaMalloc(&pl.d_rec_a, nrec * sizeof(uint4)));
+        SU_CU(cudaMalloc(&pl.d_rec_b, nrec * sizeof(uint4)));
+        SU_CU(cudaMemcpy(pl.d_rec_a, ht4.rec_a.data(), ht4.rec_a.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+        SU_CU(cudaMemcpy(pl.d_rec_b, ht4.rec_b.data(), ht4.rec_b.size() * sizeof(uint4), cudaMemcpyHostToDevice));
+        pl.tables.rec_a = pl.d_rec_a;
+        pl.tables.rec_b = pl.d_rec_b;
+        pl.has_tables = true;
+    }
     st->plans[key] = pl;
     *out = &st->plans[key];
     return 0;
@@ -451,7 +788,7 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
 
 int slos_units_layer(SlosUnitsState* st, cudaStream_t stream, int m, int k, const double2* parent, void* child,
                      const double2* U, int in_mode, const double* sqrt_tab, int write_probs, uint64_t* launches,
-                     std::string* err) {
+                     std::string* err, int version) {
     SlosLayerPlan* pl = nullptr;
     int rc = build_plan(st, m, k, &pl, err);
     if (rc) return rc;
@@ -463,7 +800,16 @@ int slos_units_layer(SlosUnitsState* st, cudaStream_t stream, int m, int k, cons
     a.n_parents = k >= 1 ? binom(host_bin(), m + k - 2, k - 1) : 1;
     const size_t smem = (size_t)m * 16 + (size_t)pl->max_tp * 16 + (size_t)((k + 2) & ~1) * 8 + (size_t)SU_DMAX * (m + 1) * 4;
     if (smem > 200 * 1024) { *err = "slos units: parent block does not fit shared memory"; return LWB_E_LIMIT; }
-    if (smem > 48 * 1024) SU_CU(cudaFuncSetAttribute(slos_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem4 = ((size_t)m * (k + 1) + (size_t)pl->max_tp) * 16;  // weights + parent block
+    if (version >= 4 && pl->has_tables && smem4 <= 200 * 1024) {  // record kernel
+        if (smem4 + 1024 > 48 * 1024)
+            SU_CU(cudaFuncSetAttribute(slos_units4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        slos_units4_kernel<<<pl->n_items, SU_THREADS, smem4, stream>>>(a, pl->tables);
+        *launches += 1;
+        SU_CU(cudaGetLastError());
+        return 0;
+    }
+    if (smem + 1024 > 48 * 1024) SU_CU(cudaFuncSetAttribute(slos_units_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     slos_units_kernel<<<pl->n_items, SU_THREADS, smem, stream>>>(a);
     *launches += 1;
     SU_CU(cudaGetLastError());
@@ -478,16 +824,22 @@ int slos_units_plan_check(int m, int k, uint64_t* children_checked) {
     if (!slos_units_supported(m, k)) return LWB_E_LIMIT;
     const uint64_t* bin = host_bin();
     Builder b;
-    b.bin = bin; b.m = m; b.k = k;
+    b.bin = bin; b.m = m; b.k = k; b.tmax = unit_tmax(binom(bin, m + k - 1, k));
     for (int d = 0; d <= SU_DMAX; ++d) b.nf_max[d] = 0;
     b.walk(0);
     if (!b.ok) return LWB_E_LIMIT;
     std::vector<uint32_t> ht((size_t)SU_DMAX * (m + 1));
     for (int r = 0; r < SU_DMAX; ++r)
         for (int v = 0; v <= m; ++v) ht[(size_t)r * (m + 1) + v] = (uint32_t)binom(bin, m - v + r - 1, r + 1);
+    SuHostTables t4;
+    const bool has4 = build_tables(bin, m, k, b, t4);
     uint64_t checked = 0, expect_start = 0;
     for (const SlosUnit& u : b.units) {
         if (u.start != expect_start) return LWB_E_ARG;
+        if (has4) {  // the sub-unit kernel's rules, replayed with the kernel's own arithmetic
+            int rc4 = check_unit_v4(bin, m, k, u, t4);
+            if (rc4) return rc4;
+        }
         expect_start += u.T;
         int x[LWB_MAX_PHOTONS + 2], depth = 0;
         for (int s = 0; s < u.np; ++s)
@@ -536,7 +888,7 @@ int slos_units_plan_check(int m, int k, uint64_t* children_checked) {
 int slos_units_plan_info(int m, int k, uint64_t* n_units, uint64_t* n_items, uint64_t* children, uint64_t* max_tp) {
     if (!slos_units_supported(m, k)) return LWB_E_LIMIT;
     Builder b;
-    b.bin = host_bin(); b.m = m; b.k = k;
+    b.bin = host_bin(); b.m = m; b.k = k; b.tmax = unit_tmax(binom(b.bin, m + k - 1, k));
     for (int d = 0; d <= SU_DMAX; ++d) b.nf_max[d] = 0;
     b.walk(0);
     if (!b.ok) return LWB_E_LIMIT;

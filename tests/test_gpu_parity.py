@@ -407,12 +407,17 @@ def test_c5_single_permanent_slices_n28(ctx):
 
 
 # ---------------------------------------------------------------- K3u (prefix-unit SLOS kernel) vs K3 (gather kernel)
+SLOS_UNITS_DEFAULT = 4
+
 @pytest.mark.parametrize("m,n,seed", [(6, 3, 1), (12, 6, 2), (8, 5, 7), (5, 7, 11), (3, 9, 4), (1, 4, 0), (16, 8, 4),
                                        (2, 12, 5), (20, 5, 6), (24, 7, 3), (30, 4, 8), (7, 1, 9), (40, 3, 2)])
-def test_slos_unit_kernel_equals_gather_kernel(ctx, lb, m, n, seed):
-    """The two SLOS layer kernels add the same terms in the same order with the same rounding, so the AMPLITUDES are
-    bit-identical (incl. bunched inputs); probabilities (x*x + y*y vs hypot(x, y)**2) agree to 4 ulp.  Both are
-    compared with the oracle's restatement of SLOSBackend.calculate (slos.py:82-138)."""
+@pytest.mark.parametrize("version", [1, 4])
+def test_slos_unit_kernel_equals_gather_kernel(ctx, lb, m, n, seed, version):
+    """The SLOS layer kernels add the same terms in the same order.  Version 1 (child-indexed units) also rounds like
+    the gather kernel, so its AMPLITUDES are bit-identical (incl. bunched inputs) and the probabilities (x*x + y*y vs
+    hypot(x, y)**2) agree to 4 ulp; version 4 (host-built records, sqrt(mult) folded into the weights) agrees to
+    rounding.  All are compared
+    with the oracle's restatement of SLOSBackend.calculate (slos.py:82-138)."""
     U = O.random_unitary(m, seed)  # noqa: N806
     rng = np.random.default_rng(seed)
     ins = np.bincount(rng.integers(0, m, n), minlength=m).astype(np.uint8)
@@ -420,14 +425,23 @@ def test_slos_unit_kernel_equals_gather_kernel(ctx, lb, m, n, seed):
     try:
         lb.set_option("slos_units", 0)
         a_old, p_old = ctx.slos_amplitudes(U, ins), ctx.slos_basis_probs(U, ins)
-        lb.set_option("slos_units", 1)
+        lb.set_option("slos_units", version)  # 1: child-indexed units (K3u), 4: sub-units with head / tail tables
         a_new, p_new = ctx.slos_amplitudes(U, ins), ctx.slos_basis_probs(U, ins)
+        a_fock_order = ctx.slos_amplitudes(U, ins, order=0) if lb.fock_count(m, n) <= 50000 else None
     finally:
-        lb.set_option("slos_units", 1)
-    assert np.array_equal(a_new, a_old)
-    assert rel_close(p_new, p_old, 1e-15, 0.0)
-    if lb.fock_count(m, n) <= 50000:
-        assert np.array_equal(ctx.slos_amplitudes(U, ins, order=0), _reorder(lb, m, n, a_new))
+        lb.set_option("slos_units", SLOS_UNITS_DEFAULT)
+    if version == 1:
+        assert np.array_equal(a_new, a_old)
+        assert rel_close(p_new, p_old, 1e-15, 0.0)
+    else:
+        # same terms, same order, same separately rounded products; sqrt(mult) is folded into the unitary's column
+        # instead of the parent amplitude: rounding-level differences where a multiplicity > 1 occurs, none elsewhere
+        scale = max(1.0, float(np.max(np.abs(a_old))))
+        assert float(np.max(np.abs(a_new - a_old))) <= 1e-14 * scale
+        assert float(np.max(np.abs(p_new - p_old))) <= 1e-14 * scale * scale
+        assert abs(float(p_new.sum()) - float(p_old.sum())) <= 1e-12
+    if a_fock_order is not None:
+        assert np.array_equal(a_fock_order, _reorder(lb, m, n, a_new))
     if lb.fock_count(m, n) <= 20000:
         keys, amps = O.slos_calculate(U, ins)
         assert rel_close(a_new, amps, 1e-12, 1e-18)

@@ -1,6 +1,8 @@
 #!/bin/bash
-# round 2, GPU call 14: source-level ncu capture of the K1x fused kernel on C3
+# K3u v4 (sub-units): bit-identity against the gather kernel, then timing v3 vs v4
+set -x
 mkdir -p gpurun_out
-python tools/k1x_profile.py > gpurun_out/r2_k1x_plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k1x_fused -s 1 -c 1 -o gpurun_out/r2_prof_k1x -f python tools/k1x_profile.py > gpurun_out/r2_k1x_ncu.log 2>&1
-echo "ncu exit=$?"; tail -3 gpurun_out/r2_k1x_plain.log
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "slos" > gpurun_out/c14_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/c14_pytest.log
+tail -5 gpurun_out/c14_pytest.log
+for u in 1 4 1 4; do python tools/slos_profile.py 5 1 $u; done > gpurun_out/c14_slos.log 2>&1
+cat gpurun_out/c14_slos.log
