@@ -172,7 +172,7 @@ bool prefix_work(int m, int n, uint64_t rank, uint64_t total_states, unsigned __
 }  // namespace
 
 // per-state cost of classification, unranking and block prologue in units of one Glynn term (sharding.STATE_OVERHEAD_TERMS)
-static const double kStateOverheadTerms = 63.0;
+static const double kStateOverheadTerms = 150.0;
 
 extern "C" int lwb_shard_cuts(int m, int n, int n_fractions, const double* fractions, uint64_t* cuts) {
     if (!fractions || !cuts || n_fractions < 1) return fail(LWB_E_ARG, "null argument");

@@ -107,9 +107,11 @@ def cumulative_work(m: int, n: int, rank: int, overhead: float = 0.0) -> float:
     return work + overhead * rank
 
 
-# per-state cost of classification, unranking and block prologue in units of one Glynn term: fitted to the per-rank
-# kernel times of the 8-GPU C3 run on B200 (ranks holding more, cheaper states ran longer with a smaller constant)
-STATE_OVERHEAD_TERMS = 63.0
+# per-state cost of classification, unranking and block prologue in units of one Glynn term: least-squares fit of
+# time = a * terms + b * states to the 14 per-rank kernel times of the 2 / 4 / 8-GPU C3 runs on B200 (b / a = 152; with
+# the round-1 constant 63 the rank holding the most, cheapest states ran 5 % longer than the others once the walk
+# itself got faster)
+STATE_OVERHEAD_TERMS = 150.0
 
 
 def work_cuts(m: int, n: int, fractions: list[float]) -> list[int]:
