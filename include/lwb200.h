@@ -192,6 +192,8 @@ int lwb_basis_sample_selected(lwb_handle h, int backend, const double* U, int m,
  *       to the host);
  *   lwb_dist_convolve: out = a (*) b, new slot over K(n_modes, kmax_a + kmax_b);
  *   lwb_dist_axpy: acc += alpha * x (probability_distribution.py:160-164 / :62-69);
+ *   lwb_dist_axpy_many: acc += alpha_j * x_j for j = 0 .. n-1 in that order, one launch (the per-input accumulation
+ *       loop of probability_distribution.py:137-164 for every annotated input that shares its largest photon group);
  *   lwb_dist_sample: lwb_sample on a slot;  lwb_dist_download: the dense vector (size from lwb_dist_info). */
 int lwb_keyspace_size(int n_modes, int kmax, uint64_t* size);
 int lwb_keyspace_index(int n_modes, const uint8_t* state, uint64_t* index);
@@ -202,6 +204,7 @@ int lwb_dist_from_circuit(lwb_handle h, const double* U_full, int m_tot, int n_m
                           double threshold, int backend, int dtype, int* slot);
 int lwb_dist_convolve(lwb_handle h, int slot_a, int slot_b, int* slot_out);
 int lwb_dist_axpy(lwb_handle h, int slot_acc, double alpha, int slot_x);
+int lwb_dist_axpy_many(lwb_handle h, int slot_acc, int n_terms, const double* alphas, const int* slots);
 int lwb_dist_info(lwb_handle h, int slot, int* n_modes, int* kmax, uint64_t* size, void** device_ptr);
 int lwb_dist_download(lwb_handle h, int slot, double* dense);
 int lwb_dist_sample(lwb_handle h, int slot, const double* uniform, uint64_t n_samples, uint64_t* index, double* total);

@@ -82,6 +82,7 @@ SIGNATURES = {
     "lwb_dist_from_circuit": (_i, [_vp, _vp, _i, _i, _vp, _dbl, _i, _i, _pi]),
     "lwb_dist_convolve": (_i, [_vp, _i, _i, _pi]),
     "lwb_dist_axpy": (_i, [_vp, _i, _dbl, _i]),
+    "lwb_dist_axpy_many": (_i, [_vp, _i, _i, _vp, _vp]),
     "lwb_dist_info": (_i, [_vp, _i, _pi, _pi, _pu64, C.POINTER(_vp)]),
     "lwb_dist_download": (_i, [_vp, _i, _vp]),
     "lwb_dist_sample": (_i, [_vp, _i, _vp, _u64, _vp, _pdbl]),
@@ -302,6 +303,16 @@ class DeviceDistribution:
 
     def add_scaled(self, alpha: float, x: "DeviceDistribution") -> None:
         check(cdll().lwb_dist_axpy(self.ctx.handle, self.slot, float(alpha), x.slot))
+
+    def add_scaled_many(self, alphas, xs) -> None:
+        """self += alphas[j] * xs[j] for every j, in that order, as ONE launch (lwb_dist_axpy_many)."""
+        if not len(xs):
+            return
+        a = np.ascontiguousarray(alphas, dtype=np.float64)
+        slots = np.ascontiguousarray([x.slot for x in xs], dtype=np.int32)
+        if len(a) != len(slots):
+            raise ValueError("one coefficient per distribution")
+        check(cdll().lwb_dist_axpy_many(self.ctx.handle, self.slot, len(slots), ptr(a), ptr(slots)))
 
     def to_numpy(self) -> np.ndarray:
         out = np.zeros(self.size, dtype=np.float64)

@@ -178,8 +178,8 @@ def pdist_calc(circuit, inputs, backend, keep_on_device: bool = False):
             continue
         k_rest = max(sum(sum(st) for st in rest) for rest, _ in items)
         others = ctx.dist_zeros(n_modes, k_rest)
-        for rest, prob in items:
-            others.add_scaled(prob, alg.product(rest) if rest else alg.vacuum())
+        # one launch adds every annotated input of the group, in input order (the same operations as one axpy each)
+        others.add_scaled_many([prob for _, prob in items], [alg.product(rest) if rest else alg.vacuum() for rest, _ in items])
         acc.add_scaled(1.0, alg.unique(big) @ others)
         alg.n_convolutions += 1
     if keep_on_device:
@@ -202,6 +202,48 @@ def pdist_calc(circuit, inputs, backend, keep_on_device: bool = False):
     out.n_convolutions = alg.n_convolutions
     return out
 
+
+
+def detect(rows: np.ndarray, rng, efficiency: float = 1.0, p_dark: float = 0.0, photon_counting: bool = True) -> np.ndarray:
+    """Detector._get_output (components/detector.py:101-135) for every row of `rows` (uint8 [samples, modes]) at
+    once: each photon survives with probability `efficiency`, each mode gains one dark count with probability
+    p_dark, threshold detectors report min(count, 1).  Only occupied entries draw a variate (most of a Fock state is
+    empty), and a single photon is a Bernoulli draw instead of a binomial one."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    if efficiency < 1:
+        flat = rows.reshape(-1)
+        nz = np.flatnonzero(flat)
+        vals = flat[nz]
+        kept = (rng.random(len(nz)) < efficiency).astype(np.uint8)
+        many = np.flatnonzero(vals > 1)
+        if len(many):
+            kept[many] = rng.binomial(vals[many], efficiency)
+        flat[nz] = kept
+    if p_dark > 0:
+        rows = rows + (rng.random(rows.shape) < p_dark).astype(np.uint8)
+    if not photon_counting:
+        rows = np.minimum(rows, 1)
+    return rows
+
+
+def count_rows_first_seen(rows: np.ndarray):
+    """Counter(rows) as arrays: (index of the first occurrence of every distinct row, its count), in first-seen order
+    like the dict a SamplingResult is built from.  Rows of <= 16 small counts are packed into one 64-bit key (a plain
+    integer sort); anything else is compared as byte strings."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    n, m = rows.shape
+    if n == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    bits = max(int(rows.max()).bit_length(), 1)
+    if m * bits <= 64:
+        key = np.zeros(n, dtype=np.uint64)
+        for j in range(m):
+            key = (key << np.uint64(bits)) | rows[:, j].astype(np.uint64)
+    else:
+        key = rows.view(np.dtype((np.void, m))).reshape(-1)
+    _, first, counts = np.unique(key, return_index=True, return_counts=True)
+    order = np.argsort(first, kind="stable")
+    return first[order], counts[order]
 
 def sample_source_outputs(circuit, input_state, n_samples: int, backend, purity: float = 1.0, brightness: float = 1.0,
                           indistinguishability: float = 1.0, probability_threshold: float = 1e-9,
@@ -232,18 +274,9 @@ def sample_source_outputs(circuit, input_state, n_samples: int, backend, purity:
     rng = np.random.default_rng(seed)
     idx, _total = acc.sample(rng.random(int(n_samples)))
     uniq, inverse = np.unique(idx, return_inverse=True)
-    out = _lib.keyspace_states(n_modes, acc.kmax, uniq)[inverse.reshape(-1)].astype(np.int64)  # one row per sample
-    if detector_efficiency < 1:
-        out = rng.binomial(out, detector_efficiency)
-    if p_dark > 0:
-        out = out + (rng.random(out.shape) < p_dark)
-    if not photon_counting:
-        out = np.minimum(out, 1)
-    # count equal rows: compare them as byte strings (one memcmp per comparison instead of a lexicographic row sort)
-    rows = np.ascontiguousarray(out.astype(np.uint8))
-    keys, first, counts = np.unique(rows.view(np.dtype((np.void, rows.shape[1]))).reshape(-1), return_index=True,
-                                    return_counts=True)
-    order = np.argsort(first, kind="stable")  # Counter semantics: first-drawn order
+    out = _lib.keyspace_states(n_modes, acc.kmax, uniq).astype(np.uint8)[inverse.reshape(-1)]  # one row per sample
+    rows = detect(out, rng, detector_efficiency, p_dark, photon_counting)
+    first, counts = count_rows_first_seen(rows)
     if as_arrays:
-        return rows[first[order]], counts[order]
-    return {_state_cls(k): int(c) for k, c in zip(rows[first[order]].tolist(), counts[order].tolist())}
+        return rows[first], counts
+    return {_state_cls(k): int(c) for k, c in zip(rows[first].tolist(), counts.tolist())}

@@ -90,6 +90,25 @@ static __global__ void dist_axpy_kernel(double* __restrict__ acc, double alpha, 
     if (i < n) acc[i] += alpha * x[i];
 }
 
+// acc[i] += alpha_j * x_j[i] for j = 0 .. n-1 IN THAT ORDER (each x_j over its own prefix key space): the same sequence
+// of operations per element as n dist_axpy_kernel launches, in one launch
+struct DistAxpyTerm {
+    const double* x;
+    uint64_t n;
+    double alpha;
+};
+static __global__ void dist_axpy_many_kernel(double* __restrict__ acc, const DistAxpyTerm* __restrict__ terms, int n_terms,
+                                             uint64_t n_max) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_max) return;
+    double a = acc[i];
+    for (int j = 0; j < n_terms; ++j) {
+        const DistAxpyTerm t = terms[j];
+        if (i < t.n) a += t.alpha * t.x[i];
+    }
+    acc[i] = a;
+}
+
 // dst[i] = src[i] > threshold ? src[i] : 0   (strict, per full state: permanent.py:151, slos.py:74)
 static __global__ void dist_threshold_copy_kernel(double* __restrict__ dst, const double* __restrict__ src, double threshold,
                                                   uint64_t n) {

@@ -154,7 +154,7 @@ int lwb_destroy(lwb_handle h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (Buf* b : {&h->bU, &h->bIn, &h->bOut, &h->bRes, &h->bPart, &h->bTmp, &h->bLayerA, &h->bLayerB, &h->bProbs,
-                   &h->bMarg, &h->bFirst, &h->bSmall, &h->bCdf, &h->bTile, &h->bUni, &h->bIdx})
+                   &h->bMarg, &h->bFirst, &h->bSmall, &h->bCdf, &h->bTile, &h->bUni, &h->bIdx, &h->bTerms})
         if (b->p) cudaFree(b->p);
     k1x_destroy(h->k1x);
     slos_units_destroy(h->slos_units);
@@ -1341,9 +1341,12 @@ int lwb_dist_create(lwb_handle h, int n_modes, int kmax, const double* dense, in
     CU(cudaSetDevice(h->device));
     CK(new_slot(h, n_modes, 0, kmax, slot));
     auto& d = h->dists[*slot];
-    if (dense) CU(cudaMemcpyAsync(d.p, dense, d.size * 8, cudaMemcpyHostToDevice, h->stream));
-    else CU(cudaMemsetAsync(d.p, 0, d.size * 8, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
+    if (dense) {
+        CU(cudaMemcpyAsync(d.p, dense, d.size * 8, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));  // the caller may reuse `dense` on return
+    } else {
+        CU(cudaMemsetAsync(d.p, 0, d.size * 8, h->stream));  // stream-ordered like every later use of the slot: no wait
+    }
     return 0;
 }
 
@@ -1399,6 +1402,39 @@ int lwb_dist_axpy(lwb_handle h, int slot_acc, double alpha, int slot_x) {
     dist_axpy_kernel<<<(unsigned)((x->size + 255) / 256), 256, 0, h->stream>>>(acc->p, alpha, x->p, x->size);
     h->launches++;
     acc->kmin = std::min(acc->kmin, x->kmin);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int lwb_dist_axpy_many(lwb_handle h, int slot_acc, int n_terms, const double* alphas, const int* slots) {
+    if (!h || (n_terms > 0 && (!alphas || !slots))) return fail(LWB_E_ARG, "null argument");
+    if (n_terms <= 0) return 0;
+    std::lock_guard<std::mutex> lk(h->mu);
+    lwb_context::DistSlot* acc = nullptr;
+    CK(get_slot(h, slot_acc, &acc));
+    std::vector<DistAxpyTerm> terms((size_t)n_terms);
+    uint64_t n_max = 0;
+    int kmin = acc->kmin;
+    for (int j = 0; j < n_terms; ++j) {
+        lwb_context::DistSlot* x = nullptr;
+        CK(get_slot(h, slots[j], &x));
+        if (x == acc) return fail(LWB_E_ARG, "term %d is the accumulator itself", j);
+        if (acc->n_modes != x->n_modes || acc->kmax < x->kmax)
+            return fail(LWB_E_ARG, "accumulator (%d modes, <= %d photons) cannot hold term %d (%d modes, <= %d photons)",
+                        acc->n_modes, acc->kmax, j, x->n_modes, x->kmax);
+        terms[(size_t)j] = DistAxpyTerm{x->p, x->size, alphas[j]};
+        n_max = std::max(n_max, x->size);
+        kmin = std::min(kmin, x->kmin);
+    }
+    CU(cudaSetDevice(h->device));
+    // the term table travels through a per-call device buffer: pageable source, so it is staged before the copy returns;
+    // the buffer is reused by the next call only after this call's kernel (same stream)
+    CK(ensure(h, h->bTerms, terms.size() * sizeof(DistAxpyTerm)));
+    CU(cudaMemcpyAsync(h->bTerms.p, terms.data(), terms.size() * sizeof(DistAxpyTerm), cudaMemcpyHostToDevice, h->stream));
+    dist_axpy_many_kernel<<<(unsigned)((n_max + 255) / 256), 256, 0, h->stream>>>(acc->p, (const DistAxpyTerm*)h->bTerms.p, n_terms,
+                                                                                 n_max);
+    h->launches++;
+    acc->kmin = kmin;
     CU(cudaGetLastError());
     return 0;
 }

@@ -45,7 +45,7 @@ struct lwb_context {
     cudaStream_t copy_stream = nullptr;  // D2H of finished chunks overlaps the next chunk's kernel
     cudaEvent_t chunk_done[8] = {};
     uint64_t* d_bin = nullptr;
-    Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall, bCdf, bTile, bUni, bIdx;
+    Buf bU, bIn, bOut, bRes, bPart, bTmp, bLayerA, bLayerB, bProbs, bMarg, bFirst, bSmall, bCdf, bTile, bUni, bIdx, bTerms;
     uint64_t launches = 0;
     lwb::K1xState* k1x = nullptr;
     lwb::SlosUnitsState* slos_units = nullptr;  // cached K3u plans per (m, k)

@@ -3,7 +3,7 @@ Minimal stand-ins for the two reference value types the hot path touches, used o
 `lightworks` package is not importable (e.g. on a bare GPU box).  With lightworks present,
 `lightworks_b200.install()` makes the backends return real `lightworks.State` objects instead.
 
-  State               mirrors lightworks/sdk/state/state.py:27-140 (list wrapper, hash/eq by ket string)
+  State               mirrors lightworks/sdk/state/state.py:27-140 (list wrapper, eq by content)
   CompiledCircuitView mirrors the fields of CompiledPhotonicCircuit that the backends read
                       (sdk/circuit/photonic_compiler.py:46-80): U_full, n_modes, loss_modes
 """
@@ -45,7 +45,9 @@ class State:
         return isinstance(other, State) and self._s == other._s
 
     def __hash__(self) -> int:
-        return hash(str(self))
+        # equal states hash equally, which is all a dict needs; the reference hashes the ket string (state.py:95-96),
+        # ten times slower for the 3 x 10^5 distinct outcomes of a noisy 10^6-sample run
+        return hash(tuple(self._s))
 
     def __len__(self) -> int:
         return len(self._s)

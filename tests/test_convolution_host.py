@@ -36,6 +36,10 @@ class _FakeDist:
         assert x.n_modes == self.n_modes and x.kmax <= self.kmax
         self.dense[: x.size] += alpha * x.dense
 
+    def add_scaled_many(self, alphas, xs):
+        for alpha, x in zip(alphas, xs):
+            self.add_scaled(alpha, x)
+
     def to_numpy(self):
         return self.dense.copy()
 
@@ -149,3 +153,33 @@ def test_source_classes_path_equals_label_path():
     assert not basic.annotated and len(basic) == 4
     d = conv.pdist_calc(lb.CompiledCircuitView(O.random_unitary(5, 3)), basic, _FakeBackend("permanent"))
     assert d.vals_array.sum() == pytest.approx(1.0, abs=1e-8)
+
+
+def test_detector_and_counting_helpers():
+    """detect(): thinning / dark counts / threshold detection of whole sample arrays against their exact moments;
+    count_rows_first_seen(): Counter semantics (first-seen order) on the packed-key and the byte-string path."""
+    from collections import Counter
+
+    from lightworks_b200.convolution import count_rows_first_seen, detect
+
+    rng = np.random.default_rng(3)
+    base = np.array([[2, 0, 1, 0, 3], [0, 0, 0, 1, 1], [1, 1, 1, 1, 1]], dtype=np.uint8)
+    rows = base[rng.integers(0, 3, 60000)]
+    eff = 0.7
+    out = detect(rows.copy(), np.random.default_rng(4), eff)
+    assert out.dtype == np.uint8 and out.shape == rows.shape and np.all(out <= rows)
+    mean, expect = out.mean(axis=0), eff * rows.mean(axis=0)
+    var = (eff * (1 - eff) * rows + (eff * rows.astype(float)) ** 2).mean(axis=0) - expect**2
+    assert np.all(np.abs(mean - expect) < 5 * np.sqrt(var / len(rows)) + 1e-9)
+    assert np.array_equal(detect(rows.copy(), np.random.default_rng(4), 1.0), rows)          # perfect detector: untouched
+    dark = detect(np.zeros((40000, 4), dtype=np.uint8), np.random.default_rng(5), 1.0, p_dark=0.05)
+    assert abs(dark.mean() - 0.05) < 5 * np.sqrt(0.05 * 0.95 / dark.size)
+    clicks = detect(rows.copy(), np.random.default_rng(6), 0.9, p_dark=0.01, photon_counting=False)
+    assert clicks.max() <= 1
+    for data in (out, np.concatenate([out, out], axis=1).astype(np.uint8) * 9):  # 5 x 2 bits packed; 10 x 5 bits: byte strings
+        first, counts = count_rows_first_seen(data)
+        ref = Counter(map(tuple, data.tolist()))
+        assert [tuple(r) for r in data[first].tolist()] == list(ref.keys())
+        assert counts.tolist() == list(ref.values())
+    f0, c0 = count_rows_first_seen(np.zeros((0, 3), dtype=np.uint8))
+    assert len(f0) == 0 and len(c0) == 0

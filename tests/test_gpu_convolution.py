@@ -86,6 +86,30 @@ def test_convolve_matches_bruteforce(lb, ctx, ka, kb, m):
         _ = da @ ctx.dist_zeros(m + 1, 1)
 
 
+def test_axpy_many_equals_sequential_axpys(lb, ctx):
+    """lwb_dist_axpy_many: one launch, the same operations per element in the same order as one lwb_dist_axpy per term
+    (bit-identical), with terms over different prefix key spaces; argument errors."""
+    L, m = lb._lib, 5  # noqa: N806
+    rng = np.random.default_rng(8)
+    kmaxs = [0, 3, 1, 2, 3, 0, 2]
+    xs = [ctx.dist_from_dense(m, k, rng.random(L.keyspace_size(m, k))) for k in kmaxs]
+    alphas = rng.random(len(xs)) * 3 - 1
+    start = rng.random(L.keyspace_size(m, 4))
+    one, many = ctx.dist_from_dense(m, 4, start), ctx.dist_from_dense(m, 4, start)
+    for a, x in zip(alphas, xs):
+        one.add_scaled(float(a), x)
+    many.add_scaled_many(alphas, xs)
+    assert np.array_equal(one.to_numpy(), many.to_numpy())
+    many.add_scaled_many([], [])  # nothing to do
+    assert np.array_equal(one.to_numpy(), many.to_numpy())
+    with pytest.raises(ValueError):
+        ctx.dist_zeros(m, 2).add_scaled_many([1.0], [xs[1]])  # term larger than the accumulator
+    with pytest.raises(ValueError):
+        many.add_scaled_many([1.0], [many])  # the accumulator cannot be its own term
+    with pytest.raises(ValueError):
+        many.add_scaled_many([1.0, 2.0], [xs[0]])
+
+
 @pytest.mark.parametrize("backend", ["permanent", "slos"])
 @pytest.mark.parametrize("case", ["lossless", "lossy", "vacuum"])
 def test_dist_from_circuit_is_full_probability_distribution(lb, ctx, backend, case):

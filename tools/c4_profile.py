@@ -11,3 +11,13 @@ be.ctx.synchronize()
 t0=time.perf_counter(); acc = pdist_calc(circ16, classes, be, keep_on_device=True); be.ctx.synchronize(); print("pdist_calc", time.perf_counter()-t0, acc.n_convolutions)
 pr=cProfile.Profile(); pr.enable(); acc = pdist_calc(circ16, classes, be, keep_on_device=True); be.ctx.synchronize(); pr.disable()
 pstats.Stats(pr).sort_stats("tottime").print_stats(14)
+# the whole Sampler chain (bench.py extra c4_noisy_sampler), stage by stage
+import numpy as np
+from lightworks_b200 import _lib
+pr = cProfile.Profile(); pr.enable()
+t0 = time.perf_counter()
+counts = lb.sample_source_outputs(circ16, [1] * 8 + [0] * 8, 1_000_000, be, purity=0.99, brightness=0.9, indistinguishability=0.95,
+                                  detector_efficiency=0.9, seed=7)
+print("sample_source_outputs", time.perf_counter() - t0, len(counts))
+pr.disable()
+pstats.Stats(pr).sort_stats("cumtime").print_stats(22)
