@@ -339,6 +339,24 @@ __device__ __forceinline__ void su_add_term(double2& acc, const double2 v, const
     acc.y = __dadd_rn(acc.y, t.y);
 }
 
+#ifndef LWB_SU4_LD
+#define LWB_SU4_LD 0
+#endif
+// a prefix-stream amplitude: read once by this thread, never again by this CTA
+__device__ __forceinline__ double2 su4_stream_load(const char* p) {
+#if LWB_SU4_LD == 1
+    return __ldcs(reinterpret_cast<const double2*>(p));
+#elif LWB_SU4_LD == 2
+    return __ldg(reinterpret_cast<const double2*>(p));
+#elif LWB_SU4_LD == 3
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+#else
+    return *reinterpret_cast<const double2*>(p);
+#endif
+}
+
 // J children per thread (c0, c0 + 256, ...) of the unit `un`; children past T - 1 recompute the last one, store nothing
 template <int J>
 __device__ __forceinline__ void su4_children(const SlosUnitsArgs& a, const SuTables& tb, const SlosUnit& un, uint32_t c0,
@@ -364,7 +382,7 @@ __device__ __forceinline__ void su4_children(const SlosUnitsArgs& a, const SuTab
         if (s_ < np) {
             const char* p = reinterpret_cast<const char*>(sptr[s_]) + (uint64_t)c0 * 16u;
 #pragma unroll
-            for (int j = 0; j < J; ++j) bf[j] = *reinterpret_cast<const double2*>(p + dj[j]);
+            for (int j = 0; j < J; ++j) bf[j] = su4_stream_load(p + dj[j]);
         }
     };
 #pragma unroll
