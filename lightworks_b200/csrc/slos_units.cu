@@ -1,4 +1,6 @@
-// slos_units.cu -- K3u: SLOS layer kernel over "prefix units" (round 2).
+// slos_units.cu -- K3u / K3r: SLOS layer kernels over "prefix units" (round 2).  K3u (slos_units_kernel) derives the
+// trailing indices per child; K3r (slos_units4_kernel, the default) reads them from host-built records - see the
+// comment above that kernel.  Both share the units, the streams, the staged parent block and the host plan below.
 //
 // Same recurrence as slos_layer_kernel (slos_kernels.cuh; SLOSBackend.calculate, lightworks/emulator/backends/
 // slos.py:96-103): for the k-th input photon in mode i
@@ -27,7 +29,6 @@
 #include <cstring>
 #include <map>
 #include <string>
-#include <tuple>
 #include <vector>
 
 #include "fock.cuh"
@@ -773,7 +774,7 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
         for (int v = 0; v <= m; ++v) ht[(size_t)r * (m + 1) + v] = (uint32_t)binom(bin, m - v + r - 1, r + 1);
     pl.n_units = (uint32_t)b.units.size();
     pl.n_items = (uint32_t)items.size();
-    SuHostTables ht4;   // sub-unit kernel: tables and the units' hoff (before the units are uploaded)
+    SuHostTables ht4;   // record kernel: records and the units' rbase (before the units are uploaded)
     memset(&pl.tables, 0, sizeof pl.tables);
     const bool has4 = build_tables(bin, m, k, b, ht4);
 #define SU_CU(call)                                                                   \
@@ -854,7 +855,7 @@ int slos_units_plan_check(int m, int k, uint64_t* children_checked) {
     uint64_t checked = 0, expect_start = 0;
     for (const SlosUnit& u : b.units) {
         if (u.start != expect_start) return LWB_E_ARG;
-        if (has4) {  // the sub-unit kernel's rules, replayed with the kernel's own arithmetic
+        if (has4) {  // the record kernel's rules, replayed with the kernel's own arithmetic
             int rc4 = check_unit_v4(bin, m, k, u, t4);
             if (rc4) return rc4;
         }

@@ -14,7 +14,7 @@ bool slos_units_supported(int m, int k);
 // code with *err set (LWB_E_LIMIT: fall back to the gather-form kernel).
 int slos_units_layer(SlosUnitsState* st, cudaStream_t stream, int m, int k, const double2* parent, void* child,
                      const double2* U, int in_mode, const double* sqrt_tab, int write_probs, uint64_t* launches,
-                     std::string* err, int version = 3);  // version 4: sub-unit kernel (head / tail tables)
+                     std::string* err, int version = 3);  // version 4: record kernel (host-built records)
 int slos_units_plan_check(int m, int k, uint64_t* children_checked);
 int slos_units_plan_info(int m, int k, uint64_t* n_units, uint64_t* n_items, uint64_t* children, uint64_t* max_tp);
 }  // namespace lwb
