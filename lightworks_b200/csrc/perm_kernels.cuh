@@ -303,24 +303,30 @@ template <int N, typename T>
 __global__ void __launch_bounds__(K1_THREADS, LWB_MINB) perm_single_kernel(PermSingleArgs a) {
     using S = K2Shape<N>;
     using V = typename vec2<T>::type;
-    // the matrix and, when both fit the 48 KB of static shared memory (n <= 38 in double), its negated copy
-    constexpr bool NEG = 2 * N * N * sizeof(V) + 1024 <= 48 * 1024;
-    constexpr int neg_off = N * N;
-    __shared__ __align__(16) V Ms[(NEG ? 2 : 1) * N * N];
+    // the matrix and, when both fit the 48 KB of static shared memory (n <= 37 in double), its negated copy.
+    // Rows are RS = N | 1 elements apart: at a chunk boundary every lane flips its own row, and with an even N
+    // (n = 24: 96 words, a multiple of the 32 banks) all those rows start in the same bank - an 8-way conflict on each of
+    // the N loads, every 2^C steps (measured: n = 24 ran 38 % slower per step than n = 26).  An odd stride spreads
+    // consecutive rows over all banks.
+    constexpr int RS = N | 1;
+    constexpr bool NEG = 2 * N * RS * sizeof(V) + 1024 <= 48 * 1024;
+    constexpr int neg_off = N * RS;
+    __shared__ __align__(16) V Ms[(NEG ? 2 : 1) * N * RS];
     __shared__ int ident[N];
     __shared__ double red[2][K1_THREADS / 32];
     const int tid = threadIdx.x;
-    if (tid < N) ident[tid] = tid * N;
+    if (tid < N) ident[tid] = tid * RS;
     for (int e = tid; e < N * N; e += K1_THREADS) {
         double2 u = a.A[e];
         V v;
         v.x = (T)u.x;
         v.y = (T)u.y;
-        Ms[e] = v;
+        const int at = (e / N) * RS + e % N;
+        Ms[at] = v;
         if constexpr (NEG) {
             v.x = -v.x;
             v.y = -v.y;
-            Ms[neg_off + e] = v;
+            Ms[neg_off + at] = v;
         }
     }
     __syncthreads();
