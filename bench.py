@@ -457,7 +457,7 @@ def main() -> int:  # noqa: PLR0915
                 "traffic": traffic,
                 "traffic_note": "DRAM bytes of one fused-kernel launch (ncu): 4x the 740 MB of algorithmic output because the "
                                 "probabilities leave in bucket (multiplicity-pattern) order as scattered 8-byte stores "
-                                "(partial-sector fills) and the 370 MB bucket index is read; 3.1 GB per 98 ms = 31 GB/s, "
+                                "(partial-sector fills) and the 370 MB bucket index is read; 3.0 GB per 96 ms = 31 GB/s, "
                                 "0.5 % of the HBM peak - the kernel is FP64-bound",
                 "kernel_ms": k_ms, "flops_per_unit": flops_per_perm(N_PH), "units_per_launch": cnt,
                 "peak_source": peak_src,
