@@ -589,10 +589,16 @@ def extras(ctx, stream, peak, d_U, torch, np, O, _lib) -> dict:  # noqa: N803
     # algorithmic bytes: every layer reads its parent once and writes itself once (the last layer
     # writes 8-byte probabilities)
     slos_bytes = sum(16 * (comb(M + k - 2, k - 1) + comb(M + k - 1, k)) for k in range(1, N_PH + 1))
+    slos_traffic = None
+    try:  # DRAM bytes of the whole evolution from the committed ncu launch list
+        slos_traffic = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic.json"))).get("dram_bytes_per_evolution")
+    except Exception:
+        slos_traffic = None
     out["slos_c3"] = {"probabilities_per_s": S / (ms * 1e-3), "ms": ms, "gather_kernel_ms": ms_gather,
                       "unit_kernel_ms": ms_units,
                       "roofline": {"bound": "hbm", "achieved": slos_bytes / (ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                   "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes},
+                                   "frac": slos_bytes / (ms * 1e-3) / 1e9 / hbm, "algorithmic_bytes": slos_bytes,
+                                   "traffic": slos_traffic},
                       "gather_traffic": {"bytes": 16 * M * sum(comb(M + k - 2, k - 1) for k in range(1, N_PH + 1)),
                                          "achieved_gbs": 16 * M * sum(comb(M + k - 2, k - 1) for k in range(1, N_PH + 1)) / (ms * 1e-3) / 1e9,
                                          "note": "every (child, occupied mode) edge of a layer reads a distinct parent "
