@@ -162,6 +162,18 @@ def test_multiplicity_plan_host():
         _lib.multiplicity_plan(17)
 
 
+@pytest.mark.parametrize("m,n", [(1, 5), (2, 12), (3, 2), (3, 9), (5, 7), (6, 3), (6, 9), (7, 13), (8, 8), (10, 10),
+                                 (12, 6), (16, 8), (20, 6), (30, 5), (40, 4), (64, 3), (128, 2), (24, 8), (16, 12)])
+def test_slos_layer_plan_self_check(m, n):
+    """lwb_slos_plan_check (host only): every unit of the SLOS layer plan (m modes, n photons) replayed child by child
+    with the kernels' own index arithmetic - child rank, the parent of every prefix stream, the parent and the weight
+    of every trailing run of the unit kernel and of the record kernel - against exact lexicographic ranks.  The last
+    two shapes hold 7.9e6 / 1.7e7 children in 8192-child units with up to 8 trailing photons."""
+    info = _lib.slos_plan_check(m, n)
+    assert info["children"] == _lib.fock_count(m, n)
+    assert info["units"] >= 1 and info["items"] >= 1 and info["items"] <= info["units"]
+
+
 def test_cumulative_work_is_exact_and_cuts_balance():
     """sharding.cumulative_work against a brute-force sum over fock_basis (terms of the multiplicity-aware walk,
     csrc/k1x.h), and the bisection cuts of work_balanced_ranges."""

@@ -410,7 +410,8 @@ def test_c5_single_permanent_slices_n28(ctx):
 SLOS_UNITS_DEFAULT = 4
 
 @pytest.mark.parametrize("m,n,seed", [(6, 3, 1), (12, 6, 2), (8, 5, 7), (5, 7, 11), (3, 9, 4), (1, 4, 0), (16, 8, 4),
-                                       (2, 12, 5), (20, 5, 6), (24, 7, 3), (30, 4, 8), (7, 1, 9), (40, 3, 2)])
+                                       (2, 12, 5), (20, 5, 6), (24, 7, 3), (30, 4, 8), (7, 1, 9), (40, 3, 2),
+                                       (20, 10, 12), (16, 12, 13)])  # the last two: 2.0e7 / 1.7e7 states, 8192-child units
 @pytest.mark.parametrize("version", [1, 4])
 def test_slos_unit_kernel_equals_gather_kernel(ctx, lb, m, n, seed, version):
     """The SLOS layer kernels add the same terms in the same order.  Version 1 (child-indexed units) also rounds like
@@ -421,11 +422,12 @@ def test_slos_unit_kernel_equals_gather_kernel(ctx, lb, m, n, seed, version):
     U = O.random_unitary(m, seed)  # noqa: N806
     rng = np.random.default_rng(seed)
     ins = np.bincount(rng.integers(0, m, n), minlength=m).astype(np.uint8)
-    assert lb._lib.slos_plan_check(m, n)["children"] == lb.fock_count(m, n)
+    if lb.fock_count(m, n) <= 10**6:  # the host replay of every child's indices (the big plans: CPU suite)
+        assert lb._lib.slos_plan_check(m, n)["children"] == lb.fock_count(m, n)
     try:
         lb.set_option("slos_units", 0)
         a_old, p_old = ctx.slos_amplitudes(U, ins), ctx.slos_basis_probs(U, ins)
-        lb.set_option("slos_units", version)  # 1: child-indexed units (K3u), 4: sub-units with head / tail tables
+        lb.set_option("slos_units", version)  # 1: child-indexed units (K3u), 4: host-built records (K3r)
         a_new, p_new = ctx.slos_amplitudes(U, ins), ctx.slos_basis_probs(U, ins)
         a_fock_order = ctx.slos_amplitudes(U, ins, order=0) if lb.fock_count(m, n) <= 50000 else None
     finally:
