@@ -518,7 +518,9 @@ def main() -> int:  # noqa: PLR0915
             assert abs(complex(float(o5[0]), float(o5[1])) - complex(float(o1[0]), float(o1[1]))) <= 1e-10 * abs(complex(float(o1[0]), float(o1[1])))
             c5[f"n{n5}"] = {"ms": ms5, "ms_one_gpu": ms1, "speedup": ms1 / ms5, "efficiency": ms1 / ms5 / world,
                             "permanents_per_s": 1e3 / ms5,
-                            "fp64_frac_per_gpu": flops_per_perm(n5) / (ms5 * 1e-3) / peak / world}
+                            "fp64_frac_per_gpu": flops_per_perm(n5) / (ms5 * 1e-3) / peak / world,
+                            "path": "Gray slices + 16-byte all-reduce" if n5 >= 24 else
+                                    "every rank walks the whole space (below 24 photons the exchange costs more than it saves)"}
         line["extra"] = {"single_perm_sharded": c5}
     if rank == 0 and world == 1:
         threads = os.cpu_count() or 1

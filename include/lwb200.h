@@ -264,7 +264,8 @@ int lwb_comm_perm_basis_probs_dev(lwb_comm c, const double* d_U, int m, const ui
 int lwb_comm_pdist(lwb_comm c, const double* U_full, int m_tot, int n_modes, const uint8_t* in_state, double threshold,
                    int dtype, uint8_t* keys, double* vals, uint64_t cap, uint64_t* count_out);
 /* lwb_perm_single with the Gray-code space split over the communicator and the 16-byte sum (NCCL all-reduce for
- * RANK, fixed-order host sum for LOCAL). */
+ * RANK, fixed-order host sum for LOCAL).
+ * Below 24 photons one GPU is faster than the exchange: every rank (RANK) / device 0 (LOCAL) walks the whole space. */
 int lwb_comm_perm_single(lwb_comm c, const double* A, int n, int dtype, double* out2);
 int lwb_comm_perm_single_dev(lwb_comm c, const double* d_A, int n, int dtype, double* d_out2);
 /* lwb_dist_from_circuit for `count` input states at once (probability_distribution.py:127-133: the unique

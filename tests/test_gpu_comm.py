@@ -58,11 +58,13 @@ def _check_local(lb, n_gpus):
             keys, vals = comm.pdist(U, m - 3, lossy)  # 3 loss modes
             rk, rv = ctx.pdist(U, m - 3, lossy, 1e-9, 0)
             assert np.array_equal(keys, rk) and np.array_equal(vals, rv)
-        A = O.random_unitary(60, 5)[:22, :22]  # noqa: N806
+        A = O.random_unitary(60, 5)[:24, :24]  # noqa: N806
         want = sum(ctx.perm_single(A, slice_=s, n_slices=n_gpus) for s in range(n_gpus))
-        assert comm.perm_single(A) == want
+        assert comm.perm_single(A) == want            # n >= 24: Gray slices, partial sums added in device order
         hp = O.perm_hp(A)
         assert abs(comm.perm_single(A) - hp) <= 1e-10 * abs(hp)
+        A = A[:21, :21]                               # below 24 one device walks the whole space (no exchange pays)
+        assert comm.perm_single(A) == ctx.perm_single(A)
         # unique sub-inputs of an imperfect source, round-robin over the devices
         U = O.random_unitary(10, 4)  # noqa: N806
         subs = [[(b >> i) & 1 for i in range(5)] + [0] * 3 for b in range(32)]
