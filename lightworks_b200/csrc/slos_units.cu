@@ -26,6 +26,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -521,12 +522,22 @@ struct SlosLayerPlan {
 
 struct SlosUnitsState {
     std::map<std::pair<int, int>, SlosLayerPlan> plans;
+    size_t bytes = 0;   // device memory held by the cached plans
 };
 
-SlosUnitsState* slos_units_create() { return new SlosUnitsState(); }
-void slos_units_destroy(SlosUnitsState* st) {
-    if (!st) return;
-    for (auto& kv : st->plans) {
+// A process that sweeps many circuit shapes would otherwise keep every plan (C3's ten layers: ~30 MB) for ever: once the
+// cache passes this size it is emptied before the next plan is built (LWB_SLOS_PLAN_CACHE_MB overrides the 1 GiB).
+static size_t plan_cache_cap() {
+    static const size_t cap = [] {
+        const char* e = getenv("LWB_SLOS_PLAN_CACHE_MB");
+        const long mb = e ? atol(e) : 1024;
+        return (size_t)(mb > 0 ? mb : 1024) << 20;
+    }();
+    return cap;
+}
+
+static void free_plans(SlosUnitsState* st) {
+    for (auto& kv : st->plans) {   // cudaFree waits for the kernels that still read a plan
         cudaFree(kv.second.d_units);
         cudaFree(kv.second.d_items);
         cudaFree(kv.second.d_lut);
@@ -534,6 +545,14 @@ void slos_units_destroy(SlosUnitsState* st) {
         cudaFree(kv.second.d_rec_a);
         cudaFree(kv.second.d_rec_b);
     }
+    st->plans.clear();
+    st->bytes = 0;
+}
+
+SlosUnitsState* slos_units_create() { return new SlosUnitsState(); }
+void slos_units_destroy(SlosUnitsState* st) {
+    if (!st) return;
+    free_plans(st);
     delete st;
 }
 
@@ -727,6 +746,7 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
     auto key = std::make_pair(m, k);
     auto it = st->plans.find(key);
     if (it != st->plans.end()) { *out = &it->second; return 0; }
+    if (st->bytes > plan_cache_cap()) free_plans(st);
     const uint64_t* bin = host_bin();
     Builder b;
     b.bin = bin; b.m = m; b.k = k; b.tmax = unit_tmax(binom(bin, m + k - 1, k));
@@ -800,6 +820,8 @@ static int build_plan(SlosUnitsState* st, int m, int k, SlosLayerPlan** out, std
         pl.tables.rec_b = pl.d_rec_b;
         pl.has_tables = true;
     }
+    st->bytes += b.units.size() * sizeof(SlosUnit) + items.size() * sizeof(uint2) + std::max<size_t>(lut.size(), 1) * 8 +
+                 ht.size() * 4 + (has4 ? 2 * std::max<size_t>(ht4.rec_a.size(), 1) * sizeof(uint4) : 0);
     st->plans[key] = pl;
     *out = &st->plans[key];
     return 0;
