@@ -55,7 +55,10 @@ constexpr uint32_t SU_TMAX = LWB_SU_TMAX;   // children per unit (large layers)
 // 0.117 -> 0.091 ms), while the largest layers prefer long units (24 modes / 10 photons: 1.97 vs 2.25 ms).
 constexpr uint64_t SU_SMALL_LAYER = 16u << 20;
 static uint32_t unit_tmax(uint64_t children) { return children < SU_SMALL_LAYER ? (uint32_t)LWB_SU_TMAX_SMALL : SU_TMAX; }
-constexpr uint32_t SU_ITEM = 4096;   // a CTA takes consecutive units until it holds this many children ...
+#ifndef LWB_SU_ITEM
+#define LWB_SU_ITEM 4096
+#endif
+constexpr uint32_t SU_ITEM = LWB_SU_ITEM;   // a CTA takes consecutive units until it holds this many children ...
 constexpr uint32_t SU_ITEM_MIN = 256;  // ... fewer on small layers, so that every SM gets several CTAs
 static uint32_t item_size(uint64_t children) {
     const uint64_t per = children / (148 * 8);
